@@ -1,0 +1,324 @@
+// extern "C" boundary of libbisip_b200.so — see include/bisip_b200.h for the contract.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "common.cuh"
+#include "decomp_eval.cuh"
+#include "models.cuh"
+#include "sampler.cuh"
+#include "stats.cuh"
+
+using namespace bisip;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define BISIP_CUDA(expr)                                                                      \
+  do {                                                                                        \
+    cudaError_t e_ = (expr);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(BISIP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));        \
+  } while (0)
+
+int check_desc(const bisip_model_desc* d) {
+  if (!d) return fail(BISIP_ERR_BAD_ARG, "desc is null");
+  if (d->n_freq <= 0) return fail(BISIP_ERR_BAD_ARG, "n_freq must be positive");
+  switch (d->model) {
+    case BISIP_MODEL_COLECOLE:
+      if (d->n_modes < 1 || d->n_modes > kMaxModes)
+        return fail(BISIP_ERR_UNSUPPORTED, "ColeCole n_modes must be in [1,8]");
+      if (d->ndim != 1 + 3 * d->n_modes) return fail(BISIP_ERR_BAD_ARG, "ColeCole ndim != 1+3*n_modes");
+      break;
+    case BISIP_MODEL_DIAS:
+      if (d->ndim != 5) return fail(BISIP_ERR_BAD_ARG, "Dias2000 ndim != 5");
+      break;
+    case BISIP_MODEL_SHIN:
+      if (d->ndim != 6) return fail(BISIP_ERR_BAD_ARG, "Shin2015 ndim != 6");
+      break;
+    case BISIP_MODEL_DECOMP:
+      if (d->n_tau <= 0 || d->n_coef <= 0) return fail(BISIP_ERR_BAD_ARG, "Decomp n_tau/n_coef must be positive");
+      if (d->ndim != 1 + d->n_coef) return fail(BISIP_ERR_BAD_ARG, "Decomp ndim != 1+n_coef");
+      if (d->n_coef > 8) return fail(BISIP_ERR_UNSUPPORTED, "Decomp poly_deg > 7 not supported");
+      if (d->n_tau > 64) return fail(BISIP_ERR_UNSUPPORTED, "Decomp n_tau > 64 not supported yet");
+      if (d->precision != BISIP_PREC_FP64) return fail(BISIP_ERR_UNSUPPORTED, "only FP64 precision is built");
+      break;
+    default:
+      return fail(BISIP_ERR_BAD_ARG, "unknown model id");
+  }
+  return BISIP_OK;
+}
+
+int device_smem_optin() {
+  int dev = 0, v = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// Batched forward / log-probability kernels (same evaluators as the sampler).
+// grid (chunks, B): CTA (c, b) handles theta rows [c*kRows, ...) of spectrum b, striding by gridDim.x.
+constexpr int kRows = 128;
+
+struct BatchParams {
+  bisip_model_desc d;
+  int B, n_theta;
+  const double* theta;
+  const double* w; long long w_stride;
+  const double* taus; const double* log_taus; long long tau_stride;
+  const double* y; const double* yerr; const double* bounds;
+  double* Z; double* lp;
+};
+
+template <int KC, bool WANT_Z>
+__global__ void __launch_bounds__(kThreads) decomp_batch_kernel(const BatchParams P) {
+  extern __shared__ __align__(16) double smem[];
+  const int b = blockIdx.y, ndim = P.d.ndim, N = P.d.n_freq;
+  DecompShape sh(P.d.n_freq, P.d.n_tau, P.d.n_coef);
+  DecompSmem s;
+  double* p = decomp_carve(s, smem, sh, kRows);
+  double* prop = p; p += kRows * ndim;
+  double* chi = p; p += kRows;
+  double* bnd = p; p += 2 * ndim;
+  double* red = p;
+  if (!WANT_Z) for (int i = threadIdx.x; i < 2 * ndim; i += kThreads) bnd[i] = P.bounds[i];
+  decomp_init(s, sh, P.d.c_exp, P.w + (size_t)b * P.w_stride, P.taus + (size_t)b * P.tau_stride,
+              P.log_taus + (size_t)b * P.tau_stride * P.d.n_coef,
+              WANT_Z ? nullptr : P.y + (size_t)b * 2 * N, WANT_Z ? nullptr : P.yerr + (size_t)b * 2 * N, red);
+  for (int r0 = blockIdx.x * kRows; r0 < P.n_theta; r0 += gridDim.x * kRows) {
+    const int n = min(kRows, P.n_theta - r0);
+    const double* th = P.theta + ((size_t)b * P.n_theta + r0) * ndim;
+    for (int i = threadIdx.x; i < kRows * ndim; i += kThreads) prop[i] = (i < n * ndim) ? th[i] : 0.0;
+    __syncthreads();
+    if (WANT_Z) {
+      decomp_eval_Z<KC>(s, sh, prop, ndim, n, P.Z + ((size_t)b * P.n_theta + r0) * 2 * N);
+    } else {
+      decomp_eval_chi<KC>(s, sh, prop, ndim, n, kRows, chi);
+      __syncthreads();
+      for (int q = threadIdx.x; q < n; q += kThreads)
+        P.lp[(size_t)b * P.n_theta + r0 + q] =
+            in_bounds(prop + q * ndim, bnd, ndim) ? -0.5 * (chi[q] + s.llconst) : neg_inf();
+    }
+    __syncthreads();
+  }
+}
+
+template <class Row, bool WANT_Z>
+__global__ void __launch_bounds__(kThreads) vec_batch_kernel(const BatchParams P) {
+  extern __shared__ __align__(16) double smem[];
+  const int b = blockIdx.y, ndim = P.d.ndim, N = P.d.n_freq;
+  VecSmem s;
+  double* p = vec_carve(s, smem, N);
+  double* prop = p; p += kRows * ndim;
+  double* chi = p; p += kRows;
+  double* bnd = p; p += 2 * ndim;
+  double* red = p;
+  if (!WANT_Z) for (int i = threadIdx.x; i < 2 * ndim; i += kThreads) bnd[i] = P.bounds[i];
+  vec_init(s, N, P.w + (size_t)b * P.w_stride, WANT_Z ? nullptr : P.y + (size_t)b * 2 * N,
+           WANT_Z ? nullptr : P.yerr + (size_t)b * 2 * N, red);
+  for (int r0 = blockIdx.x * kRows; r0 < P.n_theta; r0 += gridDim.x * kRows) {
+    const int n = min(kRows, P.n_theta - r0);
+    const double* th = P.theta + ((size_t)b * P.n_theta + r0) * ndim;
+    for (int i = threadIdx.x; i < kRows * ndim; i += kThreads) prop[i] = (i < n * ndim) ? th[i] : 0.0;
+    __syncthreads();
+    if (WANT_Z) {
+      vec_eval_Z<Row>(s, N, P.d.n_modes, prop, ndim, n, P.Z + ((size_t)b * P.n_theta + r0) * 2 * N);
+    } else {
+      vec_eval_chi<Row>(s, N, P.d.n_modes, prop, ndim, n, chi);
+      __syncthreads();
+      for (int q = threadIdx.x; q < n; q += kThreads)
+        P.lp[(size_t)b * P.n_theta + r0 + q] =
+            in_bounds(prop + q * ndim, bnd, ndim) ? -0.5 * (chi[q] + s.llconst) : neg_inf();
+    }
+    __syncthreads();
+  }
+}
+
+size_t batch_smem_bytes(const bisip_model_desc& d) {
+  size_t dbl = (size_t)kRows * d.ndim + kRows + 2 * d.ndim + kWarps;
+  if (d.model == BISIP_MODEL_DECOMP)
+    dbl += decomp_smem_doubles(DecompShape(d.n_freq, d.n_tau, d.n_coef), kRows);
+  else
+    dbl += vec_smem_doubles(d.n_freq);
+  return dbl * 8;
+}
+
+template <typename K>
+int launch(K kernel, dim3 grid, size_t smem, cudaStream_t st, const char* name, const void* params_ptr) {
+  if ((int)smem > device_smem_optin())
+    return fail(BISIP_ERR_UNSUPPORTED, std::string(name) + ": problem does not fit in shared memory");
+  BISIP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void* args[] = {const_cast<void*>(params_ptr)};
+  BISIP_CUDA(cudaLaunchKernel((const void*)kernel, grid, dim3(kThreads), args, smem, st));
+  g_launches.fetch_add(1);
+  return BISIP_OK;
+}
+
+template <bool WANT_Z>
+int run_batch(const BatchParams& P, cudaStream_t st) {
+  const size_t smem = batch_smem_bytes(P.d);
+  int chunks = ceil_div(P.n_theta, kRows);
+  const int cap = max(1, (148 * 8) / max(1, P.B));   // enough CTAs to fill the chip, no more
+  if (chunks > cap) chunks = cap;
+  dim3 grid(chunks, P.B);
+  switch (P.d.model) {
+    case BISIP_MODEL_COLECOLE: return launch(vec_batch_kernel<ColeColeRow, WANT_Z>, grid, smem, st, "colecole_batch", &P);
+    case BISIP_MODEL_DIAS: return launch(vec_batch_kernel<DiasRow, WANT_Z>, grid, smem, st, "dias_batch", &P);
+    case BISIP_MODEL_SHIN: return launch(vec_batch_kernel<ShinRow, WANT_Z>, grid, smem, st, "shin_batch", &P);
+    default: {
+      const int KC = ceil_div(P.d.n_tau, 16);
+      switch (KC) {
+        case 1: return launch(decomp_batch_kernel<1, WANT_Z>, grid, smem, st, "decomp_batch", &P);
+        case 2: return launch(decomp_batch_kernel<2, WANT_Z>, grid, smem, st, "decomp_batch", &P);
+        case 3: return launch(decomp_batch_kernel<3, WANT_Z>, grid, smem, st, "decomp_batch", &P);
+        default: return launch(decomp_batch_kernel<4, WANT_Z>, grid, smem, st, "decomp_batch", &P);
+      }
+    }
+  }
+}
+
+__global__ void build_kernel_matrix(const double* w, int N, const double* taus, int S, double c_exp, double* K) {
+  double cs, sn;
+  sincospi(0.5 * c_exp, &sn, &cs);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S * N; i += gridDim.x * blockDim.x) {
+    const int k = i / N, j = i - k * N;
+    double kre, kim;
+    debye_kernel_term(w[j], taus[k], c_exp, cs, sn, kre, kim);
+    K[(size_t)k * 2 * N + j] = kre;
+    K[(size_t)k * 2 * N + N + j] = kim;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int bisip_abi_version(void) { return BISIP_ABI_VERSION; }
+const char* bisip_last_error(void) { return g_err.c_str(); }
+int64_t bisip_launch_count(void) { return g_launches.load(); }
+
+int bisip_n_keep(int nsteps, int discard, int thin) {
+  if (thin < 1 || discard < 0) return 0;
+  const int first = discard + thin - 1;
+  return nsteps <= first ? 0 : (nsteps - first + thin - 1) / thin;
+}
+
+int bisip_forward(const bisip_model_desc* desc, int n_spectra, int n_theta, const double* theta, const double* w,
+                  int64_t w_stride, const double* taus, const double* log_taus, int64_t tau_stride, double* Z,
+                  void* stream) {
+  if (int rc = check_desc(desc)) return rc;
+  if (n_spectra <= 0 || n_theta <= 0 || !theta || !w || !Z) return fail(BISIP_ERR_BAD_ARG, "bisip_forward: bad argument");
+  if (desc->model == BISIP_MODEL_DECOMP && (!taus || !log_taus)) return fail(BISIP_ERR_BAD_ARG, "bisip_forward: taus/log_taus null");
+  if (n_spectra > 65535) return fail(BISIP_ERR_UNSUPPORTED, "bisip_forward: n_spectra > 65535 per call");
+  BatchParams P{*desc, n_spectra, n_theta, theta, w, w_stride, taus, log_taus, tau_stride, nullptr, nullptr, nullptr, Z, nullptr};
+  return run_batch<true>(P, (cudaStream_t)stream);
+}
+
+int bisip_log_probability(const bisip_model_desc* desc, int n_spectra, int n_theta, const double* theta,
+                          const double* w, int64_t w_stride, const double* taus, const double* log_taus,
+                          int64_t tau_stride, const double* y, const double* yerr, const double* bounds,
+                          double* lp_out, void* stream) {
+  if (int rc = check_desc(desc)) return rc;
+  if (n_spectra <= 0 || n_theta <= 0 || !theta || !w || !y || !yerr || !bounds || !lp_out)
+    return fail(BISIP_ERR_BAD_ARG, "bisip_log_probability: bad argument");
+  if (desc->model == BISIP_MODEL_DECOMP && (!taus || !log_taus)) return fail(BISIP_ERR_BAD_ARG, "bisip_log_probability: taus/log_taus null");
+  if (n_spectra > 65535) return fail(BISIP_ERR_UNSUPPORTED, "bisip_log_probability: n_spectra > 65535 per call");
+  BatchParams P{*desc, n_spectra, n_theta, theta, w, w_stride, taus, log_taus, tau_stride, y, yerr, bounds, nullptr, lp_out};
+  return run_batch<false>(P, (cudaStream_t)stream);
+}
+
+int bisip_decomp_build_kernel(const double* w, int n_freq, const double* taus, int n_tau, double c_exp, double* K,
+                              void* stream) {
+  if (!w || !taus || !K || n_freq <= 0 || n_tau <= 0) return fail(BISIP_ERR_BAD_ARG, "bisip_decomp_build_kernel: bad argument");
+  build_kernel_matrix<<<ceil_div(n_freq * n_tau, 256), 256, 0, (cudaStream_t)stream>>>(w, n_freq, taus, n_tau, c_exp, K);
+  BISIP_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return BISIP_OK;
+}
+
+int bisip_ensemble_run(const bisip_model_desc* desc, int n_spectra, int n_walkers, int nsteps, int step0,
+                       uint64_t seed, uint32_t spectrum0, double a, int discard, int thin, const double* w,
+                       int64_t w_stride, const double* taus, const double* log_taus, int64_t tau_stride,
+                       const double* y, const double* yerr, const double* bounds, double* coords, double* lp,
+                       double* chain, double* logp, int32_t* accepted, int32_t* flags, void* stream) {
+  if (int rc = check_desc(desc)) return rc;
+  if (n_spectra <= 0 || n_walkers < 2 || nsteps < 0 || thin < 1 || discard < 0 || !w || !y || !yerr || !bounds || !coords)
+    return fail(BISIP_ERR_BAD_ARG, "bisip_ensemble_run: bad argument");
+  if (desc->model == BISIP_MODEL_DECOMP && (!taus || !log_taus)) return fail(BISIP_ERR_BAD_ARG, "bisip_ensemble_run: taus/log_taus null");
+  if (!(a > 1.0)) return fail(BISIP_ERR_BAD_ARG, "bisip_ensemble_run: stretch scale a must be > 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  EnsembleParams P;
+  P.d = *desc; P.B = n_spectra; P.W = n_walkers; P.nsteps = nsteps; P.step0 = step0; P.seed = seed;
+  P.spectrum0 = spectrum0; P.a = a; P.discard = discard; P.thin = thin;
+  P.nkeep = bisip_n_keep(nsteps, discard, thin);
+  P.w = w; P.w_stride = w_stride; P.taus = taus; P.log_taus = log_taus; P.tau_stride = tau_stride;
+  P.y = y; P.yerr = yerr; P.bounds = bounds; P.coords = coords; P.lp = lp; P.chain = chain; P.logp = logp;
+  P.accepted = accepted; P.flags = flags;
+  if (flags) BISIP_CUDA(cudaMemsetAsync(flags, 0, sizeof(int32_t) * (size_t)n_spectra, st));
+  const int rp = sampler_rows_pad(n_walkers);
+  size_t smem = sampler_smem_bytes(n_walkers, desc->ndim);
+  dim3 grid(n_spectra);
+  switch (desc->model) {
+    case BISIP_MODEL_COLECOLE:
+      smem += VecEvaluator<ColeColeRow>::smem_doubles(*desc, rp) * 8;
+      return launch(ensemble_kernel<VecEvaluator<ColeColeRow>, 1>, grid, smem, st, "ensemble_colecole", &P);
+    case BISIP_MODEL_DIAS:
+      smem += VecEvaluator<DiasRow>::smem_doubles(*desc, rp) * 8;
+      return launch(ensemble_kernel<VecEvaluator<DiasRow>, 2>, grid, smem, st, "ensemble_dias", &P);
+    case BISIP_MODEL_SHIN:
+      smem += VecEvaluator<ShinRow>::smem_doubles(*desc, rp) * 8;
+      return launch(ensemble_kernel<VecEvaluator<ShinRow>, 2>, grid, smem, st, "ensemble_shin", &P);
+    default: {
+      smem += DecompEvaluator<4>::smem_doubles(*desc, rp) * 8;
+      const int KC = ceil_div(desc->n_tau, 16);
+      switch (KC) {
+        case 1: return launch(ensemble_kernel<DecompEvaluator<1>, 2>, grid, smem, st, "ensemble_decomp", &P);
+        case 2: return launch(ensemble_kernel<DecompEvaluator<2>, 2>, grid, smem, st, "ensemble_decomp", &P);
+        case 3: return launch(ensemble_kernel<DecompEvaluator<3>, 2>, grid, smem, st, "ensemble_decomp", &P);
+        default: return launch(ensemble_kernel<DecompEvaluator<4>, 2>, grid, smem, st, "ensemble_decomp", &P);
+      }
+    }
+  }
+}
+
+int64_t bisip_column_stats_workspace(int n_spectra, int64_t n_samples, int n_cols) {
+  if (n_spectra <= 0 || n_samples <= 0 || n_cols <= 0) return 0;
+  return (int64_t)n_spectra * n_samples * n_cols * 8;
+}
+
+int bisip_column_stats(const double* data, int n_spectra, int64_t n_samples, int n_cols, int n_pct,
+                       const int64_t* pct_lo, const double* pct_gamma, double* pct_out, double* mean_out,
+                       double* std_out, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!data || n_spectra <= 0 || n_samples <= 0 || n_cols <= 0 || n_pct < 0 || !workspace)
+    return fail(BISIP_ERR_BAD_ARG, "bisip_column_stats: bad argument");
+  if (n_pct > kMaxPct) return fail(BISIP_ERR_UNSUPPORTED, "bisip_column_stats: at most 16 percentiles per call");
+  if (n_pct > 0 && (!pct_lo || !pct_gamma || !pct_out)) return fail(BISIP_ERR_BAD_ARG, "bisip_column_stats: percentile arrays null");
+  if (workspace_bytes < bisip_column_stats_workspace(n_spectra, n_samples, n_cols))
+    return fail(BISIP_ERR_BAD_ARG, "bisip_column_stats: workspace too small");
+  if (n_spectra > 65535) return fail(BISIP_ERR_UNSUPPORTED, "bisip_column_stats: n_spectra > 65535 per call");
+  cudaStream_t st = (cudaStream_t)stream;
+  StatsParams P;
+  P.data = data; P.keys = (unsigned long long*)workspace; P.n = n_samples; P.ncol = n_cols; P.B = n_spectra;
+  P.npct = n_pct;
+  for (int i = 0; i < n_pct; ++i) { P.lo[i] = pct_lo[i]; P.gamma[i] = pct_gamma[i]; }
+  P.pct_out = pct_out; P.mean_out = mean_out; P.std_out = std_out;
+  dim3 g1((unsigned)((n_samples + 4095) / 4096), n_spectra);
+  transpose_keys_kernel<<<g1, kThreads, 0, st>>>(P);
+  BISIP_CUDA(cudaGetLastError());
+  dim3 g2(n_cols, n_spectra);
+  column_select_kernel<<<g2, kThreads, 0, st>>>(P);
+  BISIP_CUDA(cudaGetLastError());
+  g_launches.fetch_add(2);
+  return BISIP_OK;
+}
+
+}  // extern "C"

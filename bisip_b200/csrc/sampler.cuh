@@ -1,0 +1,244 @@
+// On-device affine-invariant ensemble sampler: one persistent CTA per spectrum runs all
+// nsteps of emcee's red/blue stretch move (emcee is third-party and not
+// vendored in the reference — call sites models.py:111-118) with the walkers, their
+// log-probabilities and the per-spectrum model constants resident in shared memory.
+//
+// Stream layout (identical to oracle/bisip_oracle.c::oracle_ensemble_run):
+//   Philox4x32-10, key = seed, counter = (index, step, spectrum, purpose)
+//   purpose 0      shuffle keys: walker i <- word (i&3) of index (i>>2); rank by (key,i);
+//                  ranks [0,H0) = split 0, [H0,W) = split 1, H0 = (W+1)/2
+//   purpose 1+2s   proposal p of split s: u = u53(x,y) -> zz = ((a-1)u+1)^2/a ; partner = mulhi(z, Nc)
+//   purpose 2+2s   proposal p of split s: acceptance draw u53(x,y)
+#pragma once
+#include "common.cuh"
+#include "decomp_eval.cuh"
+#include "models.cuh"
+
+namespace bisip {
+
+struct EnsembleParams {
+  bisip_model_desc d;
+  int B, W, nsteps, step0;
+  unsigned long long seed;
+  uint32_t spectrum0;
+  double a;
+  int discard, thin, nkeep;
+  const double* w; long long w_stride;
+  const double* taus; const double* log_taus; long long tau_stride;
+  const double* y; const double* yerr; const double* bounds;
+  double* coords; double* lp; double* chain; double* logp;
+  int* accepted; int* flags;
+};
+
+struct SamplerSmem {
+  double* coords;  // [W][ndim]
+  double* lp;      // [W]
+  double* prop;    // [rows_pad][ndim]
+  double* chi;     // [rows_pad]
+  double* fac;     // [rows_pad]  (ndim-1) ln zz
+  double* bnd;     // [2][ndim]
+  double* red;     // [kWarps]
+  uint32_t* keys;  // [W]
+  int* list;       // [W]   walker at rank
+  int* acc;        // [W]
+  int* inb;        // [rows_pad]
+};
+
+__host__ __device__ inline int sampler_rows_pad(int W) { return ceil_div((W + 1) / 2, 16) * 16; }
+
+__host__ __device__ inline size_t sampler_smem_bytes(int W, int ndim) {
+  const int rp = sampler_rows_pad(W);
+  size_t dbl = (size_t)W * ndim + W + (size_t)rp * ndim + rp + rp + 2 * ndim + kWarps;
+  size_t ints = (size_t)W * 3 + rp;
+  return dbl * 8 + ints * 4 + 16;
+}
+
+__device__ inline void sampler_carve(SamplerSmem& s, double* base, int W, int ndim) {
+  const int rp = sampler_rows_pad(W);
+  s.coords = base; base += (size_t)W * ndim;
+  s.lp = base; base += W;
+  s.prop = base; base += (size_t)rp * ndim;
+  s.chi = base; base += rp;
+  s.fac = base; base += rp;
+  s.bnd = base; base += 2 * ndim;
+  s.red = base; base += kWarps;
+  s.keys = reinterpret_cast<uint32_t*>(base);
+  s.list = reinterpret_cast<int*>(s.keys + W);
+  s.acc = s.list + W;
+  s.inb = s.acc + W;
+}
+
+// strict box prior, models.py:64-69 (NaN -> outside)
+__device__ __forceinline__ bool in_bounds(const double* th, const double* bnd, int ndim) {
+  bool ok = true;
+  for (int d = 0; d < ndim; ++d) ok = ok && (bnd[d] < th[d]) && (th[d] < bnd[ndim + d]);
+  return ok;
+}
+
+// Evaluator adaptors -------------------------------------------------------------------
+template <int KC>
+struct DecompEvaluator {
+  DecompSmem sm;
+  DecompShape sh;
+  int rows_pad;
+  __device__ DecompEvaluator(const bisip_model_desc& d) : sh(d.n_freq, d.n_tau, d.n_coef) {}
+  static __host__ size_t smem_doubles(const bisip_model_desc& d, int rows_pad) {
+    return decomp_smem_doubles(DecompShape(d.n_freq, d.n_tau, d.n_coef), rows_pad);
+  }
+  __device__ double* carve(double* base, int rp) { rows_pad = rp; return decomp_carve(sm, base, sh, rp); }
+  __device__ void init(const bisip_model_desc& d, const double* w, const double* taus, const double* log_taus,
+                       const double* y, const double* yerr, double* red) {
+    decomp_init(sm, sh, d.c_exp, w, taus, log_taus, y, yerr, red);
+  }
+  __device__ double llconst() const { return sm.llconst; }
+  __device__ void eval_chi(const double* prop, int ndim, int nrows, double* chi) {
+    decomp_eval_chi<KC>(sm, sh, prop, ndim, nrows, rows_pad, chi);
+  }
+};
+
+template <class Row>
+struct VecEvaluator {
+  VecSmem sm;
+  int N, n_modes;
+  __device__ VecEvaluator(const bisip_model_desc& d) : N(d.n_freq), n_modes(d.n_modes) {}
+  static __host__ size_t smem_doubles(const bisip_model_desc& d, int) { return vec_smem_doubles(d.n_freq); }
+  __device__ double* carve(double* base, int) { return vec_carve(sm, base, N); }
+  __device__ void init(const bisip_model_desc&, const double* w, const double*, const double*, const double* y,
+                       const double* yerr, double* red) {
+    vec_init(sm, N, w, y, yerr, red);
+  }
+  __device__ double llconst() const { return sm.llconst; }
+  __device__ void eval_chi(const double* prop, int ndim, int nrows, double* chi) {
+    vec_eval_chi<Row>(sm, N, n_modes, prop, ndim, nrows, chi);
+  }
+};
+
+template <class Eval, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) ensemble_kernel(const EnsembleParams P) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x;
+  const int W = P.W, ndim = P.d.ndim;
+  const int rows_pad = sampler_rows_pad(W);
+  const int H0 = (W + 1) / 2;
+
+  Eval ev(P.d);
+  SamplerSmem s;
+  double* p = ev.carve(smem, rows_pad);
+  sampler_carve(s, p, W, ndim);
+
+  // ---- per-spectrum constants + initial ensemble ---------------------------------------
+  for (int i = tid; i < 2 * ndim; i += kThreads) s.bnd[i] = P.bounds[i];
+  const double* gc = P.coords + (size_t)b * W * ndim;
+  for (int i = tid; i < W * ndim; i += kThreads) s.coords[i] = gc[i];
+  for (int i = tid; i < W; i += kThreads) s.acc[i] = 0;
+  for (int i = tid; i < rows_pad * ndim; i += kThreads) s.prop[i] = 0.0;
+  ev.init(P.d, P.w + (size_t)b * P.w_stride, P.taus + (size_t)b * P.tau_stride,
+          P.log_taus + (size_t)b * P.tau_stride * P.d.n_coef, P.y + (size_t)b * 2 * P.d.n_freq,
+          P.yerr + (size_t)b * 2 * P.d.n_freq, s.red);   // ends with __syncthreads()
+  const double llc = ev.llconst();
+  int flag = 0;
+
+  // log-probability of p0, in two passes of <= H0 rows
+  for (int pass = 0; pass < 2; ++pass) {
+    const int off = pass ? H0 : 0, n = pass ? W - H0 : H0;
+    for (int i = tid; i < n * ndim; i += kThreads) s.prop[i] = s.coords[off * ndim + i];
+    __syncthreads();
+    ev.eval_chi(s.prop, ndim, n, s.chi);
+    __syncthreads();
+    for (int q = tid; q < n; q += kThreads) {
+      const double v = in_bounds(s.prop + q * ndim, s.bnd, ndim) ? -0.5 * (s.chi[q] + llc) : neg_inf();
+      if (v != v) flag |= 2;
+      s.lp[off + q] = v;
+    }
+    __syncthreads();
+  }
+
+  const uint32_t k0 = (uint32_t)P.seed, k1 = (uint32_t)(P.seed >> 32);
+  const uint32_t spec = P.spectrum0 + (uint32_t)b;
+  const int first = P.discard + P.thin - 1;
+  const double am1 = P.a - 1.0, dm1 = (double)ndim - 1.0;
+  int kept = 0;
+
+  for (int it = 0; it < P.nsteps; ++it) {
+    const uint32_t t = (uint32_t)(P.step0 + it);
+    // ---- random equal split (emcee: shuffle(arange(W) % 2)) ------------------------------
+    for (int i = tid; i < W; i += kThreads) {
+      const u32x4 r = philox4x32_10((uint32_t)(i >> 2), t, spec, 0u, k0, k1);
+      const int sel = i & 3;
+      s.keys[i] = sel == 0 ? r.x : sel == 1 ? r.y : sel == 2 ? r.z : r.w;
+    }
+    __syncthreads();
+    for (int i = tid; i < W; i += kThreads) {
+      const uint32_t ki = s.keys[i];
+      int rank = 0;
+      for (int j = 0; j < W; ++j) {
+        const uint32_t kj = s.keys[j];
+        rank += (kj < ki) || (kj == ki && j < i);
+      }
+      s.list[rank] = i;
+    }
+    __syncthreads();
+
+    for (int sp = 0; sp < 2; ++sp) {
+      const int off = sp ? H0 : 0, Hs = sp ? W - H0 : H0;
+      const int coff = sp ? 0 : H0, Nc = W - Hs;
+      // ---- stretch proposals q = c_j - (c_j - s_k) zz -------------------------------------
+      for (int q = tid; q < Hs; q += kThreads) {
+        const u32x4 r = philox4x32_10((uint32_t)q, t, spec, (uint32_t)(1 + 2 * sp), k0, k1);
+        const double u = u53(r.x, r.y);
+        const double zr = __dadd_rn(__dmul_rn(am1, u), 1.0);
+        const double zz = __ddiv_rn(__dmul_rn(zr, zr), P.a);
+        const int j = s.list[coff + (int)__umulhi(r.z, (uint32_t)Nc)];
+        const int k = s.list[off + q];
+        const double* cj = s.coords + j * ndim;
+        const double* sk = s.coords + k * ndim;
+        double* dst = s.prop + q * ndim;
+        for (int d = 0; d < ndim; ++d) dst[d] = __dsub_rn(cj[d], __dmul_rn(__dsub_rn(cj[d], sk[d]), zz));
+        s.fac[q] = __dmul_rn(dm1, log(zz));
+        s.inb[q] = in_bounds(dst, s.bnd, ndim) ? 1 : 0;
+      }
+      __syncthreads();
+      // ---- fused forward + chi^2 for all proposals ------------------------------------------
+      ev.eval_chi(s.prop, ndim, Hs, s.chi);
+      __syncthreads();
+      // ---- accept / reject ---------------------------------------------------------------------
+      for (int q = tid; q < Hs; q += kThreads) {
+        const u32x4 r = philox4x32_10((uint32_t)q, t, spec, (uint32_t)(2 + 2 * sp), k0, k1);
+        const double lu = log(u53(r.x, r.y));
+        const int k = s.list[off + q];
+        const double lpn = s.inb[q] ? -0.5 * (s.chi[q] + llc) : neg_inf();
+        if (lpn != lpn) flag |= 1;
+        const double lnpdiff = __dsub_rn(__dadd_rn(s.fac[q], lpn), s.lp[k]);
+        if (lnpdiff > lu) {
+          for (int d = 0; d < ndim; ++d) s.coords[k * ndim + d] = s.prop[q * ndim + d];
+          s.lp[k] = lpn;
+          s.acc[k] += 1;
+        }
+      }
+      __syncthreads();
+    }
+    // ---- backend.save_step: chain[it] = coords ; log_prob[it] = lp -----------------------------
+    if (it >= first && (it - first) % P.thin == 0) {
+      if (P.chain != nullptr) {
+        double* dst = P.chain + ((size_t)b * P.nkeep + kept) * W * ndim;
+        for (int i = tid; i < W * ndim; i += kThreads) __stcs(dst + i, s.coords[i]);
+      }
+      if (P.logp != nullptr) {
+        double* dst = P.logp + ((size_t)b * P.nkeep + kept) * W;
+        for (int i = tid; i < W; i += kThreads) __stcs(dst + i, s.lp[i]);
+      }
+      ++kept;
+    }
+  }
+  // ---- final state ------------------------------------------------------------------------------
+  double* gco = P.coords + (size_t)b * W * ndim;
+  for (int i = tid; i < W * ndim; i += kThreads) gco[i] = s.coords[i];
+  for (int i = tid; i < W; i += kThreads) {
+    if (P.lp) P.lp[(size_t)b * W + i] = s.lp[i];
+    if (P.accepted) P.accepted[(size_t)b * W + i] = s.acc[i];
+  }
+  if (P.flags && flag) atomicOr(P.flags + b, flag);
+}
+
+}  // namespace bisip

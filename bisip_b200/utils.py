@@ -1,0 +1,125 @@
+"""Chain post-processing and data ingest mixin — host-side mirror of reference ``utils.py``.
+
+Same method names, argument meaning, warnings and errors as the reference
+(``utils.py:17-146``); the reductions themselves run on the GPU:
+
+* ``get_param_percentile / mean / std`` -> ``bisip_column_stats`` (exact order statistics
+  with NumPy's 'linear' rule, so percentiles are bit-identical to ``np.percentile``)
+* ``get_model_percentile`` -> one batched ``bisip_forward`` over the whole flat chain
+  (the reference loops ``forward`` in Python once per sample, ``utils.py:32-34``) followed
+  by ``bisip_column_stats`` over the 2N model columns.
+"""
+import warnings
+
+import numpy as np
+
+from . import _lib, engine
+
+
+class utils(object):
+
+    # ---------------------------------------------------------------- percentiles of the model
+    def get_model_percentile(self, p=[2.5, 50, 97.5], chain=None, **kwargs):
+        """Percentiles of the forward model over an MCMC chain -> (len(p), 2, N).
+        Mirrors reference ``utils.py:17-35``."""
+        chain = self.parse_chain(chain, **kwargs)
+        dev = _lib.require_cuda(getattr(self, "device", None))
+        th = _lib.dev_f64(chain, dev).reshape(1, -1, chain.shape[-1])
+        Z = engine.forward(self._spec(dev), th, _lib.dev_f64(self.data['w'], dev))   # (1, n, 2, N)
+        n, N = Z.shape[1], Z.shape[3]
+        out = engine.column_stats(Z.reshape(1, n, 2 * N), p=p)["pct"][0]
+        res = out.reshape(-1, 2, N).cpu().numpy()
+        return res if np.ndim(p) else res[0]
+
+    # ---------------------------------------------------------------- parameter statistics
+    def _chain_stats(self, chain, p=None, mean=False, std=False):
+        dev = _lib.require_cuda(getattr(self, "device", None))
+        flat = _lib.dev_f64(chain, dev).reshape(1, -1, chain.shape[-1])
+        return engine.column_stats(flat, p=p, want_mean=mean, want_std=std)
+
+    def get_param_percentile(self, p=[2.5, 50, 97.5], chain=None, **kwargs):
+        """Percentiles of the parameters over a chain -> (len(p), ndim).  Ref ``utils.py:37-53``."""
+        chain = self.parse_chain(chain, **kwargs)
+        res = self._chain_stats(chain, p=p)["pct"][0].cpu().numpy()
+        return res if np.ndim(p) else res[0]
+
+    def get_param_mean(self, chain=None, **kwargs):
+        """Mean of the parameters over a chain -> (ndim,).  Ref ``utils.py:55-69``."""
+        chain = self.parse_chain(chain, **kwargs)
+        return self._chain_stats(chain, mean=True)["mean"][0].cpu().numpy()
+
+    def get_param_std(self, chain=None, **kwargs):
+        """Population standard deviation (ddof=0) -> (ndim,).  Ref ``utils.py:71-85``."""
+        chain = self.parse_chain(chain, **kwargs)
+        return self._chain_stats(chain, std=True)["std"][0].cpu().numpy()
+
+    def parse_chain(self, chain, **kwargs):
+        """Same contract as reference ``utils.py:87-106``."""
+        if chain is None:
+            kwargs['flat'] = True
+            chain = self.get_chain(**kwargs)
+            if 'discard' not in kwargs and 'thin' not in kwargs:
+                warnings.warn(('No samples were discarded from the chain.\n'
+                               'Pass discard and thin keywords to remove '
+                               'burn-in samples and reduce autocorrelation.'),
+                              UserWarning)
+        else:
+            if chain.ndim > 2:
+                raise ValueError('Flatten chain by passing flat=True.')
+            if 'discard' in kwargs or 'thin' in kwargs:
+                raise ValueError('Please pass either a chain obtained with '
+                                 'the get_chain() method or pass '
+                                 'discard and thin keywords to parse '
+                                 'the full chain. Do not pass both.')
+        return chain
+
+    # ---------------------------------------------------------------- data ingest
+    def load_data(self, filename, headers=1, ph_units='mrad'):
+        """Read one SIP spectrum (CSV: freq, amp, pha, amp_err, pha_err) and normalise it.
+        Host NumPy code with the reference's arithmetic (``utils.py:108-146``)."""
+        return prepare_data(np.loadtxt(f'{filename}', skiprows=headers, delimiter=','), ph_units)
+
+    def print_latex_parameters(self, names, values, uncertainties, decimals=3):
+        """Pretty-print parameters with LaTeX in a notebook (reference ``utils.py:148-187``).
+        Unlike the reference, models without a symbol table print their plain names."""
+        from IPython.display import display, Math
+        symbols = {
+            'PeltonColeCole': {'\\r0': '\\rho_0', '\\m': 'm_', '\\c': 'c_', '\\log_tau': '\\log\\tau_'},
+            'Dias2000': {'\\r0': '\\rho_0', '\\m': 'm', '\\log_tau': '\\log\\tau'},
+        }.get(type(self).__name__, {})
+        for n, v, u in zip(names, values, uncertainties):
+            txt = '\\{0}: {1:.{3}f} \\pm {2:.{3}f}'.format(n, v, u, decimals)
+            for old, new in symbols.items():
+                txt = txt.replace(old, new)
+            display(Math(txt))
+
+
+def prepare_data(table, ph_units='mrad'):
+    """(n, 5) table of [freq, amp, pha, amp_err, pha_err] -> the reference's data dict.
+
+    Keys (reference ``utils.py:121-144``): freq, amp, pha, amp_err, pha_err, Z, Z_err,
+    norm_factor, zn, zn_err, N, w.  Error propagation and normalisation follow the
+    reference operation by operation so that ``zn`` / ``zn_err`` are bit-identical.
+    """
+    table = np.asarray(table, dtype=np.float64)
+    names = ['freq', 'amp', 'pha', 'amp_err', 'pha_err']
+    data = {name: table[:, i] for i, name in enumerate(names)}
+    if ph_units == 'mrad':
+        data['pha'] = data['pha'] / 1000
+        data['pha_err'] = data['pha_err'] / 1000
+    if ph_units == 'deg':
+        data['pha'] = np.radians(data['pha'])
+        data['pha_err'] = np.radians(data['pha_err'])
+    amp, pha = data['amp'], data['pha']
+    data['Z'] = amp * (np.cos(pha) + 1j * np.sin(pha))
+    err_im = np.sqrt(((amp * np.cos(pha) * data['pha_err']) ** 2) + (np.sin(pha) * data['amp_err']) ** 2)
+    err_re = np.sqrt(((amp * np.sin(pha) * data['pha_err']) ** 2) + (np.cos(pha) * data['amp_err']) ** 2)
+    data['Z_err'] = err_re + 1j * err_im
+    data['norm_factor'] = max(abs(data['Z']))
+    zn = data['Z'] / data['norm_factor']
+    zn_e = data['Z_err'] / data['norm_factor']
+    data['zn'] = np.array([zn.real, zn.imag])
+    data['zn_err'] = np.array([zn_e.real, zn_e.imag])
+    data['N'] = len(data['freq'])
+    data['w'] = 2 * np.pi * data['freq']
+    return data

@@ -1,0 +1,128 @@
+"""GPU parity tests: CUDA path (through the C ABI) vs the golden vectors generated from the
+reference and vs the C oracle, on identical theta and data.
+
+Tolerances (north_star: forward and log-prob within 1e-12 relative in FP64 mode):
+  forward  : max|dZ| / max|Z| per theta           <= 1e-12
+  log-prob : |dlp| / max(1,|lp|)                   <= 1e-12 ; -inf must match exactly
+"""
+import numpy as np
+import pytest
+
+from helpers import CASES, lp_err, make_model, normwise, oracle_problem
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_forward_matches_reference_golden(case, gold_fl, data_files):
+    m = make_model(case, data_files['SIP-K389175'])
+    th = gold_fl[f'{case}/theta']
+    Z = m.forward(th, m.data['w'])
+    assert Z.shape == gold_fl[f'{case}/Z'].shape
+    assert normwise(Z, gold_fl[f'{case}/Z']).max() <= TOL
+    z1 = m.forward(th[0], m.data['w'])           # single theta -> (2, N), like the reference
+    assert z1.shape == (2, m.data['N'])
+    np.testing.assert_array_equal(z1, Z[0])
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_log_probability_matches_reference_golden(case, gold_fl, data_files):
+    m = make_model(case, data_files['SIP-K389175'])
+    th = gold_fl[f'{case}/theta']
+    ref = gold_fl[f'{case}/lp']
+    lp = m._log_probability(th, m.forward, m.param_bounds, m.data['w'], m.data['zn'], m.data['zn_err'])
+    assert np.array_equal(np.isneginf(lp), np.isneginf(ref))
+    assert np.isneginf(ref).sum() >= 8          # outside + on-face thetas are in the fixture
+    assert lp_err(lp, ref).max() <= TOL
+    # scalar call returns a float, log-likelihood ignores the prior
+    assert isinstance(m._log_probability(th[0], m.forward, m.param_bounds, m.data['w'], m.data['zn'],
+                                         m.data['zn_err']), float)
+    ll = m._log_likelihood(th, m.forward, m.data['w'], m.data['zn'], m.data['zn_err'])
+    fin = np.isfinite(ref)
+    assert lp_err(ll[fin], ref[fin]).max() <= TOL
+    assert np.all(np.isfinite(ll))
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_forward_and_logprob_match_oracle(case, gold_fl, gold_ld, data_files):
+    prob = oracle_problem(case, gold_fl, gold_ld)
+    m = make_model(case, data_files['SIP-K389175'])
+    rng = np.random.default_rng(7)
+    lo, hi = gold_fl[f'{case}/bounds']
+    th = rng.uniform(lo, hi, (300, lo.shape[0]))
+    assert normwise(m.forward(th, m.data['w']), prob.forward(th)).max() <= TOL
+    lp = m._log_probability(th, m.forward, m.param_bounds, m.data['w'], m.data['zn'], m.data['zn_err'])
+    assert lp_err(lp, prob.log_probability(th)).max() <= TOL
+
+
+def test_survey_known_answers(gold_fl, data_files):
+    """SURVEY.md App. C.1 log-probabilities."""
+    known = {'decomp_p4_debye': 384.579610803116, 'decomp_p4_warburg': -26.40360134097351,
+             'colecole_k2': 119.69117931325292, 'dias': 113.72993198177019, 'shin': -325.39343206612887}
+    for case, val in known.items():
+        m = make_model(case, data_files['SIP-K389175'])
+        th = gold_fl[f'{case}/theta'][0]
+        lp = m._log_probability(th, m.forward, m.param_bounds, m.data['w'], m.data['zn'], m.data['zn_err'])
+        assert abs(lp - val) <= 1e-12 * max(1, abs(val))
+    m = make_model('decomp_p4_debye', data_files['SIP-K389175'])
+    th = gold_fl['decomp_p4_debye/theta'][0].copy()
+    th[0] = 1.1                                   # exactly on the upper bound -> strict prior
+    assert m._log_probability(th, m.forward, m.param_bounds, m.data['w'], m.data['zn'],
+                              m.data['zn_err']) == -np.inf
+
+
+def test_raw_kernels_other_frequencies(gold_fl, data_files):
+    """forward(theta, w) must honour the w argument (SURVEY App. C.1 raw kernel calls)."""
+    import bisip_b200 as bb
+    fp = data_files['SIP-K389175']
+    w = gold_fl['raw/w']
+    cc = bb.PeltonColeCole(fp, n_modes=1).forward(np.array([1.0, 0.3, -2.0, 0.5]), w)
+    di = bb.Dias2000(fp).forward(np.array([1.0, 0.25, -10.0, 5.0, 0.5]), w)
+    sh = bb.Shin2015(fp).forward(np.array([0.5, 0.5, -14.0, -6.0, 0.5, 0.5]), w)
+    for got, key in ((cc, 'colecole'), (di, 'dias'), (sh, 'shin')):
+        assert normwise(got[None], gold_fl[f'raw/{key}'][None]).max() <= TOL
+
+
+SYN = ['syn_decomp_s64', 'syn_colecole', 'syn_dias', 'syn_shin']
+
+
+@pytest.mark.parametrize("tag", SYN)
+def test_synthetic_batch_logprob(tag, gold_fl):
+    """Batched C-ABI call over 4 spectra x n theta at the bench shape (N=64)."""
+    import torch
+    from bisip_b200 import _lib, engine, synthetic
+    from bisip_b200.batch import BatchInversion
+    model = tag.split('_')[1]
+    _, w = synthetic.frequencies(64)
+    kw = dict(poly_deg=4, n_tau=64) if model == 'decomp' else {}
+    inv = BatchInversion(model, w, gold_fl[f'{tag}/zn'], gold_fl[f'{tag}/zn_err'], **kw)
+    dev = inv.device
+    th = gold_fl[f'{tag}/theta']
+    thb = _lib.dev_f64(np.broadcast_to(th, (4,) + th.shape).copy(), dev)
+    spec = inv._spec()
+    Z = engine.forward(spec, thb, _lib.dev_f64(w, dev)).cpu().numpy()
+    for b in range(4):
+        assert normwise(Z[b], gold_fl[f'{tag}/Z']).max() <= TOL
+    lp = engine.log_probability(spec, thb, _lib.dev_f64(w, dev), _lib.dev_f64(gold_fl[f'{tag}/zn'], dev),
+                                _lib.dev_f64(gold_fl[f'{tag}/zn_err'], dev),
+                                _lib.dev_f64(gold_fl[f'{tag}/bounds'], dev)).cpu().numpy()
+    ref = gold_fl[f'{tag}/lp']
+    assert np.array_equal(np.isneginf(lp), np.isneginf(ref))
+    assert lp_err(lp, ref).max() <= TOL
+    torch.cuda.synchronize()
+
+
+def test_decomp_kernel_matrix(gold_fl, gold_ld):
+    """K = 1 - 1/(1+(i w tau)^c) against NumPy complex arithmetic."""
+    from bisip_b200 import _lib, engine
+    dev = _lib.require_cuda()
+    w = gold_ld['SIP-K389175/w']
+    for case, c in (('decomp_p4_debye', 1.0), ('decomp_p4_warburg', 0.5), ('decomp_p3_c07', 0.7)):
+        taus = gold_fl[f'{case}/taus']
+        K = engine.decomp_kernel_matrix(_lib.dev_f64(w, dev), _lib.dev_f64(taus, dev), c).cpu().numpy()
+        ref = 1 - 1 / (1 + (1j * w[None, :] * taus[:, None]) ** c)
+        N = len(w)
+        assert np.max(np.abs(K[:, :N] - ref.real)) <= 1e-14
+        assert np.max(np.abs(K[:, N:] - ref.imag)) <= 1e-14
