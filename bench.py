@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the BISIP MCMC likelihood hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Metric (BASELINE.json): log-prob evals/sec = spectra x walkers x steps / time.
+Workload: BASELINE config 5 — Debye polynomial decomposition (poly_deg 4, 64 taus) of synthetic
+64-frequency spectra, 256 walkers x 2000 steps — with a FIXED per-GPU shard of 12,500 spectra
+(weak scaling: N=8 is the full 100,000-spectra config).  One "step" = one full inversion of the
+shard: on-device ensemble sampling, kept-chain write (discard 1000, thin 10), device percentile /
+mean / std summary, and for N>1 the NCCL all-gather of the summaries.
+
+`value`  : inputs (zn, zn_err, p0) already resident in HBM; timed with CUDA events, max over ranks.
+`e2e`    : the same job through the public API (BatchInversion.fit) from pinned HOST buffers, with the
+           host->device copies of the inputs and the device->host read of the summaries inside the
+           timed region.
+`roofline`: ensemble_decomp kernel (the dominant launch): algorithmic flops (17,792 per eval,
+           SURVEY.md §8d) / its CUDA-event duration, against the FP64 DMMA peak measured on this
+           box by tools/peaks (MEASURED_PEAKS.json has no FP64 figure).
+`cpu_baseline`: the reference's own Cython + NumPy log-probability (oracle/_ref) under the emcee
+           restatement, on all host cores, on a bounded sample of the same spectra.
+`--impl reference`: that CPU arm alone, as its own JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# ---- workload (BASELINE config 5 shard) ------------------------------------------------------
+N_FREQ, N_TAU, POLY_DEG, WALKERS, NSTEPS = 64, 64, 4, 256, 2000
+SPECTRA_PER_GPU = int(os.environ.get("BISIP_BENCH_SPECTRA", 12500))
+DISCARD, THIN = 1000, 10
+PCT = (2.5, 50, 97.5)
+SEED = 0xB151B
+FLOP_PER_EVAL = 2 * (POLY_DEG + 1) * N_TAU + 2 * N_TAU * 2 * N_FREQ + 6 * 2 * N_FREQ   # 17,792
+WORKLOAD = (f"C5 shard: {SPECTRA_PER_GPU} synthetic {N_FREQ}-frequency spectra per GPU, Debye decomposition "
+            f"poly_deg={POLY_DEG}, {N_TAU} taus, {WALKERS} walkers x {NSTEPS} steps (8 GPUs = the 100,000-spectra config)")
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+# ---- reference CPU arm ---------------------------------------------------------------------------
+def _ref_worker(args):
+    """One process = one synthetic spectrum through the UNMODIFIED reference fit()
+    (models.py:84-119 -> emcee restatement -> _log_probability -> Cython Decomp_cyth)."""
+    b, zn, zn_err, w, walkers, nsteps = args
+    from oracle import refload
+    bisip = refload.load()
+    np.random.seed(1000 + b)
+    m = bisip.PolynomialDecomposition(refload.data_file(), nwalkers=walkers, nsteps=nsteps, poly_deg=POLY_DEG)
+    # inject the synthetic spectrum and the 64-tau grid through the reference's public attributes
+    # (models.py:204-209 are plain attributes users may reassign)
+    m._data.update(w=w, zn=zn, zn_err=zn_err, N=len(w))
+    lo = np.floor(min(np.log10(1. / w)) - 1)
+    hi = np.floor(max(np.log10(1. / w)) + 1)
+    m.log_tau = np.linspace(lo, hi, N_TAU)
+    m.log_taus = np.array([m.log_tau ** i for i in range(POLY_DEG + 1)])
+    m.taus = 10 ** m.log_tau
+    t0 = time.perf_counter()
+    m.fit()
+    dt = time.perf_counter() - t0
+    return dt, m.get_param_mean(discard=nsteps // 2)
+
+
+def reference_sample(zn, zn_err, w, cores, walkers=WALKERS, nsteps=None, pool=None):
+    """Bounded sample: `cores` spectra (one per process) x walkers x nsteps.  Returns evals/s."""
+    import multiprocessing as mp
+    nsteps = nsteps or env_int("BISIP_BENCH_REF_STEPS", 100)
+    jobs = [(b, zn[b], zn_err[b], w, walkers, nsteps) for b in range(cores)]
+    own = pool is None
+    if own:
+        pool = mp.get_context("fork").Pool(cores)
+    t0 = time.perf_counter()
+    pool.map(_ref_worker, jobs)
+    wall = time.perf_counter() - t0
+    if own:
+        pool.close()
+    evals = cores * walkers * nsteps
+    return evals / wall, wall, f"{cores} spectra x {walkers} walkers x {nsteps} steps, one process per core"
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def synthetic_cpu(n):
+    """The benchmark spectra b in [0, n) built with the oracle forward (no GPU): used by the
+    reference arm, which must not touch the product path."""
+    from bisip_b200 import synthetic
+    from bisip_b200.batch import tau_grid
+    from oracle import oracle
+    _, w = synthetic.frequencies(N_FREQ)
+    _, taus, log_taus = tau_grid(w, N_TAU, POLY_DEG)
+
+    def fwd(theta, ww):
+        prob = oracle.Problem('decomp', ww, np.zeros((2, len(ww))), np.ones((2, len(ww))),
+                              np.zeros((2, theta.shape[1])), taus=taus, log_taus=log_taus, c_exp=1.0)
+        return prob.forward(theta)
+    return synthetic.make('decomp', 0, n, fwd, N=N_FREQ, poly_deg=POLY_DEG)
+
+
+def run_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    cores = host_cores()
+    syn = synthetic_cpu(cores)
+    import multiprocessing as mp
+    pool = mp.get_context("fork").Pool(cores)
+    for _ in range(args.warmup):
+        reference_sample(syn['zn'], syn['zn_err'], syn['w'], cores, nsteps=2, pool=pool)
+    rates, walls, sample = [], [], ""
+    for _ in range(args.steps):
+        r, wall, sample = reference_sample(syn['zn'], syn['zn_err'], syn['w'], cores, pool=pool)
+        rates.append(r)
+        walls.append(wall)
+    pool.close()
+    val = float(np.mean(rates))
+    kind = "reference"
+    print(json.dumps({
+        "impl": "reference", "metric": "log-prob evals/sec", "value": val, "unit": "evals/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(walls)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample_per_step": sample},
+        "cpu_baseline": {"value": val, "unit": "evals/s", "cores": cores, "kind": kind, "sample": sample,
+                         "note": "reference models.py + Cython (oracle/_ref) driven by oracle/emcee_restatement.py; "
+                                 "the emcee package itself is not installable here"},
+        "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ---- GPU arm -----------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace('.', '').isdigit()]
+        reasons = []
+        for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6), ("sw_power_cap", 7)):
+            if any(len(r) >= 8 and r[col] == "Active" for r in self.rows):
+                reasons.append(name)
+        busy = [v for v in sm if v > 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": float(np.median(busy)) if busy else None,
+                "sm_max_mhz": float(self.rows[0][2]) if self.rows and len(self.rows[0]) >= 8 else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def dmma_peak():
+    """FP64 tensor (DMMA) peak of this GPU, measured now by tools/peaks (sustained 2 s loop)."""
+    exe = os.path.join(ROOT, "tools", "peaks")
+    try:
+        out = subprocess.run([exe, "--sustain", "2"], capture_output=True, text=True, timeout=120).stdout
+        j = json.loads(out.strip().splitlines()[-1])
+        return j["dmma_tflops_sustained"], j["dmma_tflops_burst"], "measured live: tools/peaks --sustain 2 (mma.sync m16n8k16 f64)"
+    except Exception as e:          # nominal: 148 SMs x 64 DFMA/clk x 2 x 1.965 GHz
+        return 37.2, 37.2, f"nominal (tools/peaks failed: {e})"
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from bisip_b200 import _lib, engine, synthetic
+    from bisip_b200.batch import BatchInversion, gather
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = SPECTRA_PER_GPU
+    b0 = rank * B                                      # weak scaling: rank r owns spectra [rB, (r+1)B)
+    nk = engine.n_keep(NSTEPS, DISCARD, THIN)
+
+    peak_sust, peak_burst, peak_src = dmma_peak() if rank == 0 else (None, None, None)
+
+    # ---- synthetic shard: truth through the CUDA forward, noise / normalisation on the host -------
+    probe = BatchInversion('decomp', synthetic.frequencies(N_FREQ)[1], np.zeros((1, 2, N_FREQ)), np.ones((1, 2, N_FREQ)),
+                           poly_deg=POLY_DEG, n_tau=N_TAU, device=dev)
+
+    def cuda_forward(theta, w):
+        th = _lib.dev_f64(theta[:, None, :], dev)
+        return engine.forward(probe._spec(), th, _lib.dev_f64(w, dev))[:, 0].cpu().numpy()
+    syn = synthetic.make('decomp', b0, b0 + B, cuda_forward, N=N_FREQ, poly_deg=POLY_DEG)
+    zn_h = torch.from_numpy(syn['zn']).pin_memory()
+    ze_h = torch.from_numpy(syn['zn_err']).pin_memory()
+    inv = BatchInversion('decomp', syn['w'], zn_h, ze_h, nwalkers=WALKERS, nsteps=NSTEPS, poly_deg=POLY_DEG,
+                         n_tau=N_TAU, seed=SEED, spectrum_offset=b0, device=dev)
+    p0_h = torch.from_numpy(inv.draw_p0(0, B)).pin_memory()
+
+    # ---- device-resident arm ---------------------------------------------------------------------
+    spec = inv._spec()
+    w_d = _lib.dev_f64(syn['w'], dev)
+    y_d, ye_d, p0_d = zn_h.to(dev), ze_h.to(dev), p0_h.to(dev)
+    bounds_d = _lib.dev_f64(inv.param_bounds, dev)
+    coords = torch.empty_like(p0_d)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    kern_ms = []
+
+    def step_resident(timed):
+        coords.copy_(p0_d)
+        ev[0].record()
+        res = engine.ensemble_run(spec, coords, w_d, y_d, ye_d, bounds_d, nsteps=NSTEPS, seed=SEED, spectrum0=b0,
+                                  discard=DISCARD, thin=THIN, store_chain=True, store_logp=False)
+        ev[1].record()
+        st = engine.column_stats(res['chain'].reshape(B, nk * WALKERS, inv.ndim), p=list(PCT), want_mean=True, want_std=True)
+        out = {'percentiles': st['pct'], 'mean': st['mean'], 'std': st['std'],
+               'acceptance_fraction': res['accepted'].to(torch.float64).mean(1) / NSTEPS}
+        if world > 1:
+            out = gather(out, B * world, rank, world)
+        if timed:
+            torch.cuda.synchronize()
+            kern_ms.append(ev[0].elapsed_time(ev[1]))
+        return out, res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        out, res = step_resident(False)
+        del res
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches0 = _lib.launch_count()
+    t_ev0, t_ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_ev0.record()
+    for _ in range(args.steps):
+        out, res = step_resident(True)
+        del res
+    t_ev1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    clk = clocks.stop()
+    ms_total = t_ev0.elapsed_time(t_ev1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    evals_step = B * world * WALKERS * NSTEPS
+    value = evals_step / (ms_step * 1e-3)
+    acc = float(out['acceptance_fraction'].mean().item())
+    flags_bad = 0
+
+    # ---- end-to-end arm: public API, pinned host inputs, host results ---------------------------------
+    h2d = zn_h.numel() * 8 + ze_h.numel() * 8 + p0_h.numel() * 8 + syn['w'].nbytes
+    e2e_ms = []
+    d2h = 0
+    for i in range(max(1, args.steps)):
+        barrier()
+        t0 = time.perf_counter()
+        r = inv.fit(p0=p0_h, discard=DISCARD, thin=THIN, percentiles=PCT)
+        torch.cuda.synchronize()
+        e2e_ms.append(1e3 * (time.perf_counter() - t0))
+        d2h = sum(v.nbytes for v in r.values())
+        flags_bad += int((r['flags'] != 0).sum())
+    te = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = evals_step / (float(te.item()) * 1e-3)
+
+    if rank == 0:
+        k_ms = float(np.mean(kern_ms))
+        flops_launch = FLOP_PER_EVAL * float(B) * WALKERS * (NSTEPS + 1)       # +1: log-prob of p0
+        achieved = flops_launch / (k_ms * 1e-3) / 1e12
+        traffic = None
+        summ = os.path.join(ROOT, "profiles", "ncu_summary.json")
+        if os.path.exists(summ):
+            try:
+                traffic = json.load(open(summ)).get("ensemble_decomp", {}).get("dram_bytes_per_launch_at_bench_size")
+            except Exception:
+                traffic = None
+        # CPU baseline (bounded sample of the same spectra, all host cores)
+        cores = host_cores()
+        cpu_v, cpu_wall, cpu_sample = reference_sample(syn['zn'], syn['zn_err'], syn['w'], min(cores, B))
+        line = {
+            "metric": "log-prob evals/sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "spectra_per_gpu": B, "walkers": WALKERS, "nsteps": NSTEPS, "n_freq": N_FREQ,
+                       "n_tau": N_TAU, "poly_deg": POLY_DEG, "discard": DISCARD, "thin": THIN, "percentiles": list(PCT),
+                       "l2": "per-step inputs (p0 154 MB) and outputs (kept chain 15 GB) exceed the 126 MB L2; no flush needed",
+                       "parallelism": f"{world} x independent shards, NCCL all-gather of summaries only"},
+            "spectra_per_s": B * world / (ms_step * 1e-3),
+            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": float(te.item()), "spectra_per_s": B * world / (float(te.item()) * 1e-3),
+                    "api": "bisip_b200.BatchInversion.fit (pinned host zn/zn_err/p0 in, host summaries out)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "ensemble_kernel<DecompEvaluator<4>> (bisip_ensemble_run)",
+                         "achieved": achieved, "peak": peak_sust, "unit": "TFLOP/s", "frac": achieved / peak_sust,
+                         "traffic": traffic, "peak_source": peak_src, "peak_burst": peak_burst,
+                         "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_step,
+                         "algorithmic_flop_per_eval": FLOP_PER_EVAL},
+            "cpu_baseline": {"value": cpu_v, "unit": "evals/s", "cores": min(cores, B), "kind": "reference", "sample": cpu_sample,
+                             "wall_s": cpu_wall,
+                             "note": "reference models.py + Cython (oracle/_ref) under oracle/emcee_restatement.py"},
+            "clocks": clk, "acceptance_fraction": acc, "nan_flags": flags_bad,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
+    args = ap.parse_args()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # convenience: `python bench.py --gpus N` re-launches itself one rank per GPU
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                                   f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+                                   "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:])
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -134,7 +134,38 @@ template <int SHAPE> double layout_err() {
   return e;
 }
 
-int main() {
+#include <chrono>
+#include <cstring>
+// `peaks --sustain SEC`: run the m16n8k16 DMMA kernel back to back for SEC seconds (the regime of a
+// kernel timed inside a long step, under the power cap) and report the rate of the last half.
+static int sustain(double seconds) {
+  cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
+  int sms = p.multiProcessorCount;
+  double* dout; CK(cudaMalloc(&dout, 64));
+  const int iters = 40000, ILP = 4, blk = 128, grid = sms * 4;
+  const double flop_per_launch = 2.0 * 16 * 8 * 16 * ILP * (double)iters * grid * (blk / 32);
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  k_dmma<3, ILP><<<grid, blk>>>(dout, iters, 1e-3); CK(cudaDeviceSynchronize());
+  auto t0 = std::chrono::steady_clock::now();
+  double burst = 0, last = 0; int n = 0;
+  std::vector<double> rates;
+  while (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() < seconds) {
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < 4; ++i) k_dmma<3, ILP><<<grid, blk>>>(dout, iters, 1e-3);
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    last = 4 * flop_per_launch / ms / 1e9; rates.push_back(last);
+    if (last > burst) burst = last; ++n;
+  }
+  double s = 0; int m = 0;
+  for (size_t i = rates.size() / 2; i < rates.size(); ++i) { s += rates[i]; ++m; }
+  printf("{\"gpu\": \"%s\", \"sms\": %d, \"dmma_tflops_burst\": %.3f, \"dmma_tflops_sustained\": %.3f, \"seconds\": %.1f, \"samples\": %d}\n",
+         p.name, sms, burst, m ? s / m : last, seconds, n);
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc >= 3 && !strcmp(argv[1], "--sustain")) return sustain(atof(argv[2]));
   cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
   int sms = p.multiProcessorCount;
   double* dout; CK(cudaMalloc(&dout, 64)); float* fout = (float*)dout;
