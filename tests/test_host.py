@@ -1,0 +1,232 @@
+"""CPU tests of the host layer: data ingest parity, chain slicing semantics, the percentile index
+arithmetic, error contracts, the C-ABI exports, and the multi-rank shard/gather logic (gloo, 2 ranks)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+import warnings
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_load_data_matches_reference(gold_ld, data_files):
+    import bisip_b200 as bb
+    for name in ('SIP-K389170', 'SIP-K389172', 'SIP-K389173', 'SIP-K389174', 'SIP-K389175', 'SIP-K389176'):
+        d = bb.Dias2000(data_files[name]).data
+        for k in ('zn', 'zn_err', 'w', 'Z', 'Z_err'):
+            np.testing.assert_array_equal(d[k], gold_ld[f'{name}/{k}'])      # bit-identical
+        assert d['norm_factor'] == gold_ld[f'{name}/norm_factor']
+        assert d['N'] == 20 and d['zn'].shape == (2, 20)
+    for units in ('rad', 'deg'):
+        d = bb.Dias2000(data_files['SIP-K389175'], ph_units=units).data
+        np.testing.assert_array_equal(d['zn'], gold_ld[f'units_{units}/zn'])
+        np.testing.assert_array_equal(d['zn_err'], gold_ld[f'units_{units}/zn_err'])
+    d = bb.PeltonColeCole(data_files['SIP-K389172'], headers=9).data
+    np.testing.assert_array_equal(d['zn'], gold_ld['headers9/zn'])
+    assert set(d) == {'freq', 'amp', 'pha', 'amp_err', 'pha_err', 'Z', 'Z_err', 'norm_factor', 'zn', 'zn_err', 'N', 'w'}
+
+
+def test_model_surface_matches_reference(data_files, gold_fl):
+    import bisip_b200 as bb
+    fp = data_files['SIP-K389175']
+    pd = bb.PolynomialDecomposition(fp, poly_deg=4)
+    assert pd.param_names == ['r0', 'a0', 'a1', 'a2', 'a3', 'a4']
+    np.testing.assert_array_equal(pd.param_bounds, gold_fl['decomp_p4_debye/bounds'])
+    np.testing.assert_array_equal(pd.taus, gold_fl['decomp_p4_debye/taus'])
+    np.testing.assert_array_equal(pd.log_taus, gold_fl['decomp_p4_debye/log_taus'])
+    np.testing.assert_array_equal(pd.log_tau, np.linspace(-6, 2, 40))
+    assert (pd.nwalkers, pd.nsteps, pd.headers, pd.ph_units, pd.poly_deg, pd.c_exp) == (32, 5000, 1, 'mrad', 4, 1.0)
+    assert bb.PolynomialDecomposition(fp).poly_deg == 5
+    assert bb.PolynomialDecomposition(fp, n_tau=64).taus.shape == (64,)
+    cc = bb.ColeCole(fp, n_modes=2)
+    assert bb.ColeCole is bb.PeltonColeCole
+    assert cc.param_names == ['r0', 'm1', 'm2', 'log_tau1', 'log_tau2', 'c1', 'c2']
+    np.testing.assert_array_equal(cc.param_bounds, gold_fl['colecole_k2/bounds'])
+    np.testing.assert_array_equal(bb.Dias2000(fp).param_bounds, gold_fl['dias/bounds'])
+    np.testing.assert_array_equal(bb.Shin2015(fp).param_bounds, gold_fl['shin/bounds'])
+    # bounds are read from the mutable params dict on every access (reference models.py:176-179)
+    pd.params.update(a0=[-2, 2])
+    assert pd.param_bounds[0, 1] == -2
+    assert not pd.fitted and pd.p0 is None
+    with pytest.raises(AssertionError, match='Model is not fitted'):
+        pd.get_chain()
+    with pytest.raises(AssertionError):
+        pd.sampler
+    with pytest.raises(AssertionError):
+        pd.plot_traces()
+    # prior is host logic: strict inequalities, NaN -> -inf
+    b = pd.param_bounds
+    assert pd._log_prior(np.array([1.0, 0, 0, 0, 0, 0]), b) == 0.0
+    assert pd._log_prior(np.array([1.1, 0, 0, 0, 0, 0]), b) == -np.inf
+    assert pd._log_prior(np.array([np.nan, 0, 0, 0, 0, 0]), b) == -np.inf
+    assert set(bb.__all__) >= {'Inversion', 'PolynomialDecomposition', 'PeltonColeCole', 'Dias2000', 'Shin2015',
+                               'plotlib', 'test_run', 'DataFiles'}
+    assert sorted(bb.DataFiles()) == ['SIP-K389170', 'SIP-K389172', 'SIP-K389173', 'SIP-K389174', 'SIP-K389175', 'SIP-K389176']
+
+
+def test_no_cpu_fallback(data_files):
+    """Without a GPU the product path must fail loudly, never compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import bisip_b200 as bb
+    from bisip_b200._lib import BisipError
+    m = bb.Dias2000(data_files['SIP-K389175'], nwalkers=32, nsteps=10)
+    with pytest.raises(BisipError, match='no CPU fallback'):
+        m.forward(np.array([1.0, 0.25, -10, 5, 0.5]), m.data['w'])
+    with pytest.raises(BisipError):
+        m.fit()
+    with pytest.raises(NotImplementedError):
+        m._log_probability(np.zeros(5), lambda t, w: 0, m.param_bounds, m.data['w'], m.data['zn'], m.data['zn_err'])
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, 'bisip_b200')
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', src, re.M), f
+                assert 'oracle/' not in src or f == 'data.py' or 'tests/golden' in src or 'same stream as oracle' in src.lower() \
+                    or 'oracle/bisip_oracle.c' in src, f
+
+
+def test_slice_chain_emcee_semantics():
+    from bisip_b200.sampler import slice_chain
+    T, W, D = 2000, 32, 4
+    arr = np.arange(T * W * D, dtype=np.float64).reshape(T, W, D)
+    assert slice_chain(arr, T, discard=500).shape == (1500, 32, 4)          # quickstart.ipynb:173
+    flat = slice_chain(arr, T, discard=500, thin=2, flat=True)
+    assert flat.shape == (24000, 4)                                          # quickstart.ipynb:192
+    np.testing.assert_array_equal(flat, arr[501::2].reshape(-1, 4))
+    np.testing.assert_array_equal(slice_chain(arr, T, thin=10), arr[9::10])
+    assert slice_chain(arr, 100).shape == (100, 32, 4)                       # iteration bound
+    from bisip_b200 import _lib
+    lib = _lib.load()
+    for (t, d, th) in [(2000, 500, 2), (2000, 0, 1), (2000, 1000, 10), (10, 9, 1), (10, 10, 1), (7, 0, 3), (7, 2, 5)]:
+        assert lib.bisip_n_keep(t, d, th) == len(range(d + th - 1, t, th))
+
+
+def test_percentile_indices_match_numpy():
+    from bisip_b200._lib import percentile_indices
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 3, 10, 999, 25600, 512000):
+        x = np.sort(rng.standard_normal(n))
+        p = np.array([0, 2.5, 16, 33.3, 50, 84, 97.5, 99.99, 100])
+        lo, g = percentile_indices(n, p)
+        hi = np.minimum(lo + 1, n - 1)
+        a, b = x[lo], x[hi]
+        d = b - a
+        val = np.where(g >= 0.5, b - d * (1 - g), a + d * g)
+        np.testing.assert_array_equal(val, np.percentile(x, p))
+    with pytest.raises(ValueError):
+        percentile_indices(10, [101])
+
+
+def test_parse_chain_contract(data_files):
+    import bisip_b200 as bb
+    m = bb.Dias2000(data_files['SIP-K389175'])
+    with pytest.raises(ValueError, match='Flatten chain'):
+        m.parse_chain(np.zeros((4, 3, 2)))
+    with pytest.raises(ValueError, match='Do not pass both'):
+        m.parse_chain(np.zeros((4, 2)), discard=1)
+    c = np.zeros((4, 2))
+    assert m.parse_chain(c) is c
+    with pytest.raises(AssertionError):          # chain=None -> get_chain -> not fitted
+        m.parse_chain(None, discard=1)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from bisip_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'bisip_b200.h')).read()
+    declared = set(re.findall(r'^\s*(?:const\s+char\s*\*\s*|int64_t\s+|int\s+)(bisip_\w+)\s*\(', hdr, re.M))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().bisip_abi_version() == 1
+    out = subprocess.run(['nm', '-D', '--defined-only', _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert all(re.search(rf'\bT {n}\b', out) for n in declared)
+
+
+def test_walkers_independent_and_autocorr():
+    from bisip_b200.sampler import integrated_time, walkers_independent
+    rng = np.random.default_rng(1)
+    assert walkers_independent(rng.standard_normal((32, 5)))
+    assert not walkers_independent(np.ones((32, 5)))
+    x = rng.standard_normal((32, 5)); x[:, 1] = x[:, 0]
+    assert not walkers_independent(x)
+    # AR(1) with phi: tau = (1+phi)/(1-phi)
+    phi, n = 0.8, 60000
+    e = rng.standard_normal((n, 4))
+    y = np.zeros((n, 4))
+    for i in range(1, n):
+        y[i] = phi * y[i - 1] + e[i]
+    tau = integrated_time(y[:, :, None])
+    assert abs(tau[0] - 9.0) < 1.0
+
+
+def test_synthetic_generator_is_shard_independent():
+    from bisip_b200 import synthetic
+    fwd = lambda th, w: np.stack([np.stack([np.outer(t[:1], np.ones_like(w))[0], -0.1 * t[1] * np.ones_like(w)]) for t in th])
+    a = synthetic.make('dias', 0, 6, fwd, N=16)
+    b = synthetic.make('dias', 3, 6, fwd, N=16)
+    np.testing.assert_array_equal(a['zn'][3:], b['zn'])
+    np.testing.assert_array_equal(a['theta_true'][3:], b['theta_true'])
+    lo, hi = synthetic.true_box('decomp', 4)
+    assert lo[0] == 0.95 and hi[1] == 0.02 and a['zn'].shape == (6, 2, 16)
+    assert np.allclose(np.max(np.hypot(a['zn'][:, 0], a['zn'][:, 1]), axis=1), 1.0)
+
+
+def test_shard_range_partitions():
+    from bisip_b200.batch import shard_range
+    for n in (1, 7, 8, 100000, 12501):
+        for world in (1, 2, 4, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            assert max(h - l for l, h in spans) == -(-n // world)
+
+
+_GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, os.environ["BISIP_ROOT"])
+import numpy as np, torch, torch.distributed as dist
+from bisip_b200.batch import shard_range, gather
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + os.environ["PORT"],
+                        rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = dist.get_rank(), dist.get_world_size()
+n = 11
+lo, hi = shard_range(n, rank, world)
+idx = torch.arange(lo, hi, dtype=torch.float64)
+local = {"mean": idx[:, None] * torch.ones(1, 3, dtype=torch.float64),
+         "percentiles": idx[:, None, None] + torch.arange(6, dtype=torch.float64).reshape(1, 2, 3),
+         "flags": torch.arange(lo, hi, dtype=torch.int32)}
+full = gather(local, n, rank, world)
+assert full["mean"].shape == (n, 3) and full["percentiles"].shape == (n, 2, 3)
+assert torch.equal(full["mean"][:, 0], torch.arange(n, dtype=torch.float64))
+assert torch.equal(full["flags"], torch.arange(n, dtype=torch.int32))
+assert torch.equal(full["percentiles"][:, 1, 2], torch.arange(n, dtype=torch.float64) + 5)
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_gather_two_ranks_gloo(tmp_path):
+    """World-size-2 gloo run of the shard + all-gather logic that the N>1 GPU path uses with NCCL."""
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    port = str(29600 + os.getpid() % 300)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", PORT=port, BISIP_ROOT=ROOT)
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=180)
+        assert p.returncode == 0, out
+        assert "ok" in out
