@@ -11,6 +11,10 @@ all: $(LIB) tools/peaks oracle
 $(LIB): $(CSRC)/api.cu $(HDRS)
 	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CSRC)/api.cu 2> $(CSRC)/ptxas.log || (cat $(CSRC)/ptxas.log; false)
 
+# developer build with per-phase cycle counters (not shipped, not loaded by the package)
+dbg: $(CSRC)/api.cu $(HDRS)
+	$(NVCC) $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared -DBISIP_PHASE_TIMING -o $(CSRC)/libbisip_b200_dbg.so $(CSRC)/api.cu
+
 tools/peaks: tools/peaks.cu
 	$(NVCC) $(ARCH) -O3 -lineinfo -o $@ $<
 
@@ -22,4 +26,4 @@ clean:
 	rm -f $(LIB) tools/peaks $(CSRC)/ptxas.log
 	rm -rf oracle/_build
 
-.PHONY: all oracle clean
+.PHONY: all oracle clean dbg

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libbisip_b200.so")
+LIB_PATH = os.environ.get("BISIP_B200_LIB", os.path.join(_HERE, "csrc", "libbisip_b200.so"))   # env: developer builds
 
 MODEL_COLECOLE, MODEL_DIAS, MODEL_SHIN, MODEL_DECOMP = 0, 1, 2, 3
 PREC_FP64, PREC_TF32, PREC_3XTF32 = 0, 1, 2

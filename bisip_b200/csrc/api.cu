@@ -2,6 +2,8 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <cmath>
 #include <string>
 
 #include "common.cuh"
@@ -263,6 +265,19 @@ int bisip_ensemble_run(const bisip_model_desc* desc, int n_spectra, int n_walker
   P.w = w; P.w_stride = w_stride; P.taus = taus; P.log_taus = log_taus; P.tau_stride = tau_stride;
   P.y = y; P.yerr = yerr; P.bounds = bounds; P.coords = coords; P.lp = lp; P.chain = chain; P.logp = logp;
   P.accepted = accepted; P.flags = flags;
+  {
+    uint32_t km = 1;
+    while ((int)km < n_walkers) km <<= 1;
+    P.kmask = km - 1;
+    int ex;
+    P.a_pow2 = (frexp(a, &ex) == 0.5) ? 1 : 0;
+    P.inv_a = 1.0 / a;
+  }
+  {
+    // developer knob; default = a quarter of one ensemble step, estimated from the tile count
+    const char* e = getenv("BISIP_STAGGER_NS");
+    P.stagger_ns = e ? strtoull(e, nullptr, 10) : 6000ull;
+  }
   if (flags) BISIP_CUDA(cudaMemsetAsync(flags, 0, sizeof(int32_t) * (size_t)n_spectra, st));
   const int rp = sampler_rows_pad(n_walkers);
   size_t smem = sampler_smem_bytes(n_walkers, desc->ndim);

@@ -52,8 +52,8 @@ __device__ __forceinline__ void debye_kernel_term(double w, double tau, double c
 struct DecompSmem {
   double* Kf;    // [NT2][KC][2][32][2]
   double* L1;    // [2KC][2][32]   stage-1 B fragments (powers of log_tau)
-  double* ycol;  // [NT2*8]  y per column (real | imag | 0-pad)
-  double* isig;  // [NT2*8]  1/sigma per column (0 on padding)
+  double* ycol;  // [NT2*8]  y/sigma per column (real | imag | 0-pad)      [forward-only mode: unused]
+  double* isig;  // [NT2*8]  delta_c/sigma per column: 1/sigma on real columns, 0 on imaginary / padding
   double* part;  // [NG][rows_pad] partial chi (only when column groups are split over warps)
   double llconst; // sum 2*ln(sigma^2)
 };
@@ -88,18 +88,22 @@ __device__ inline void decomp_init(DecompSmem& s, const DecompShape& sh, double 
     const int p = t + 4 * q, k = 8 * j + g;
     s.L1[i] = (p < sh.D && k < S) ? log_taus[(size_t)p * S + k] : 0.0;
   }
+  // Likelihood mode (y != nullptr): the residual is produced directly by the tiles,
+  //   r_c/sigma_c = y_c/sigma_c - R0*delta_c/sigma_c + sum_k (R0*M_k) * (K_kc/sigma_c),
+  // so K is stored pre-scaled by 1/sigma_c and the accumulators start at ys_c - R0*ds_c.
+  const bool scaled = (y != nullptr);
   double csum = 0.0;
   for (int c = tid; c < (int)sh.col_doubles(); c += kThreads) {
-    double yy = 0.0, is = 0.0;
-    if (c < 2 * N && y != nullptr) {
+    double ys = 0.0, ds = 0.0;
+    if (c < 2 * N && scaled) {
       const double e = yerr[c];
-      const double s2 = e * e;
-      yy = y[c];
-      is = 1.0 / e;
-      csum += 2.0 * log(s2);
+      const double is = 1.0 / e;
+      ys = y[c] * is;
+      ds = (c < N) ? is : 0.0;
+      csum += 2.0 * log(e * e);
     }
-    s.ycol[c] = yy;
-    s.isig[c] = is;
+    s.ycol[c] = ys;
+    s.isig[c] = ds;
   }
   __syncthreads();   // Kf zero-fill complete before scatter
   double cs, sn;
@@ -108,6 +112,10 @@ __device__ inline void decomp_init(DecompSmem& s, const DecompShape& sh, double 
     const int k = i / N, j = i - k * N;
     double kre, kim;
     debye_kernel_term(w[j], taus[k], c_exp, cs, sn, kre, kim);
+    if (scaled) {
+      kre *= 1.0 / yerr[j];
+      kim *= 1.0 / yerr[N + j];
+    }
     s.Kf[kf_index(k, j, KC)] = kre;
     s.Kf[kf_index(k, N + j, KC)] = kim;
   }
@@ -129,13 +137,13 @@ __device__ __forceinline__ void decomp_stage1(const DecompSmem& s, int D, const 
   const int g = lane >> 2, t = lane & 3;
   const double* q0 = prop + (size_t)(r * 16 + g) * ndim;
   const double* q1 = q0 + 8 * ndim;
-  double a1[4];
-  a1[0] = (t < D) ? q0[1 + t] : 0.0;
-  a1[1] = (t < D) ? q1[1 + t] : 0.0;
-  a1[2] = (t + 4 < D) ? q0[5 + t] : 0.0;
-  a1[3] = (t + 4 < D) ? q1[5 + t] : 0.0;
   R0a = q0[0];
   R0b = q1[0];
+  double a1[4];   // coefficients pre-multiplied by R0: stage 2 then yields R0*z directly
+  a1[0] = (t < D) ? R0a * q0[1 + t] : 0.0;
+  a1[1] = (t < D) ? R0b * q1[1 + t] : 0.0;
+  a1[2] = (t + 4 < D) ? R0a * q0[5 + t] : 0.0;
+  a1[3] = (t + 4 < D) ? R0b * q1[5 + t] : 0.0;
 #pragma unroll
   for (int kc = 0; kc < KC; ++kc) {
 #pragma unroll
@@ -152,11 +160,10 @@ __device__ __forceinline__ void decomp_stage1(const DecompSmem& s, int D, const 
   }
 }
 
-// Stage 2 for one column tile: z[16 rows][8 cols] accumulators.
+// Stage 2 for one column tile: c[16 rows][8 cols] += (R0*M) x K'.  The caller initialises c.
 template <int KC>
 __device__ __forceinline__ void decomp_stage2_tile(const DecompSmem& s, int nt, int lane, const double (&A)[KC][8],
                                                    double (&c)[4]) {
-  c[0] = c[1] = c[2] = c[3] = 0.0;
   const double2* kf = reinterpret_cast<const double2*>(s.Kf) + (size_t)nt * KC * 64 + lane;
 #pragma unroll
   for (int kc = 0; kc < KC; ++kc) {
@@ -167,7 +174,8 @@ __device__ __forceinline__ void decomp_stage2_tile(const DecompSmem& s, int nt, 
   }
 }
 
-// chi[row] = sum_c ((y_c - R0*(delta_c - z_c)) / sigma_c)^2 for rows [0,nrows) of prop.
+// chi[row] = sum_c ((y_c - R0*(delta_c - z_c)) / sigma_c)^2 for rows [0,nrows) of prop
+// (likelihood mode of decomp_init: pre-scaled K, accumulators start at the data term).
 // Block-level; prop must be visible; on return chi[] is written but NOT yet synchronised
 // when NG==1, synchronised internally when the column tiles were split over warps.
 template <int KC>
@@ -190,20 +198,23 @@ __device__ inline void decomp_eval_chi(const DecompSmem& s, const DecompShape& s
     const int nt_end = min(sh.NT2, (cg + 1) * TPG);
 #pragma unroll 2
     for (int nt = cg * TPG; nt < nt_end; ++nt) {
-      double c[4];
-      decomp_stage2_tile<KC>(s, nt, lane, A, c);
       const int col = nt * 8 + 2 * t;
-      const double2 yy = *reinterpret_cast<const double2*>(s.ycol + col);
-      const double2 is = *reinterpret_cast<const double2*>(s.isig + col);
-      const double d0 = (col < sh.N) ? 1.0 : 0.0, d1 = (col + 1 < sh.N) ? 1.0 : 0.0;
-      double r00 = (yy.x - R0a * (d0 - c[0])) * is.x;
-      double r01 = (yy.y - R0a * (d1 - c[1])) * is.y;
-      double r10 = (yy.x - R0b * (d0 - c[2])) * is.x;
-      double r11 = (yy.y - R0b * (d1 - c[3])) * is.y;
-      chi0 = fma(r00, r00, chi0);
-      chi0 = fma(r01, r01, chi0);
-      chi1 = fma(r10, r10, chi1);
-      chi1 = fma(r11, r11, chi1);
+      const double2 ys = *reinterpret_cast<const double2*>(s.ycol + col);
+      double c[4];
+      if (nt * 8 >= sh.N) {          // tile entirely in the imaginary block: delta = 0 (warp-uniform)
+        c[0] = ys.x; c[1] = ys.y; c[2] = ys.x; c[3] = ys.y;
+      } else {
+        const double2 ds = *reinterpret_cast<const double2*>(s.isig + col);
+        c[0] = fma(-R0a, ds.x, ys.x);
+        c[1] = fma(-R0a, ds.y, ys.y);
+        c[2] = fma(-R0b, ds.x, ys.x);
+        c[3] = fma(-R0b, ds.y, ys.y);
+      }
+      decomp_stage2_tile<KC>(s, nt, lane, A, c);      // c = (y - Z)/sigma
+      chi0 = fma(c[0], c[0], chi0);
+      chi0 = fma(c[1], c[1], chi0);
+      chi1 = fma(c[2], c[2], chi1);
+      chi1 = fma(c[3], c[3], chi1);
     }
     chi0 += __shfl_xor_sync(0xffffffffu, chi0, 1);
     chi0 += __shfl_xor_sync(0xffffffffu, chi0, 2);
@@ -237,16 +248,16 @@ __device__ inline void decomp_eval_Z(const DecompSmem& s, const DecompShape& sh,
     double A[KC][8];
     double R0a, R0b;
     decomp_stage1<KC>(s, sh.D, prop, ndim, r, lane, A, R0a, R0b);
-    double c[4];
-    decomp_stage2_tile<KC>(s, nt, lane, A, c);
+    double c[4] = {0.0, 0.0, 0.0, 0.0};
+    decomp_stage2_tile<KC>(s, nt, lane, A, c);       // c = R0*z
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const int col = nt * 8 + 2 * t + e;
       if (col < 2 * sh.N) {
         const double d = (col < sh.N) ? 1.0 : 0.0;
         const int row0 = r * 16 + g, row1 = row0 + 8;
-        if (row0 < nrows) Zout[(size_t)row0 * 2 * sh.N + col] = R0a * (d - c[e]);
-        if (row1 < nrows) Zout[(size_t)row1 * 2 * sh.N + col] = R0b * (d - c[2 + e]);
+        if (row0 < nrows) Zout[(size_t)row0 * 2 * sh.N + col] = R0a * d - c[e];
+        if (row1 < nrows) Zout[(size_t)row1 * 2 * sh.N + col] = R0b * d - c[2 + e];
       }
     }
   }

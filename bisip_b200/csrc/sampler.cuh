@@ -5,8 +5,9 @@
 //
 // Stream layout (identical to oracle/bisip_oracle.c::oracle_ensemble_run):
 //   Philox4x32-10, key = seed, counter = (index, step, spectrum, purpose)
-//   purpose 0      shuffle keys: walker i <- word (i&3) of index (i>>2); rank by (key,i);
-//                  ranks [0,H0) = split 0, [H0,W) = split 1, H0 = (W+1)/2
+//   purpose 0      shuffle keys: walker i <- word (i&3) of index (i>>2), low bits replaced by i so
+//                  that keys are unique: key = (word & ~mask) | i, mask = 2^ceil(log2 W) - 1;
+//                  walkers ranked by key; ranks [0,H0) = split 0, [H0,W) = split 1, H0 = (W+1)/2
 //   purpose 1+2s   proposal p of split s: u = u53(x,y) -> zz = ((a-1)u+1)^2/a ; partner = mulhi(z, Nc)
 //   purpose 2+2s   proposal p of split s: acceptance draw u53(x,y)
 #pragma once
@@ -15,6 +16,19 @@
 #include "models.cuh"
 
 namespace bisip {
+
+// Developer build (-DBISIP_PHASE_TIMING, `make dbg`): block 0 accumulates SM cycles per phase and
+// prints them at the end.  Compiled out of the product library.
+#ifdef BISIP_PHASE_TIMING
+#define PHASE_DECL long long ph_[6] = {0, 0, 0, 0, 0, 0}; long long ph_t_ = clock64();
+#define PHASE_MARK(i) { long long n_ = clock64(); ph_[i] += n_ - ph_t_; ph_t_ = n_; }
+#define PHASE_PRINT if (blockIdx.x == 0 && threadIdx.x == 0) printf("phase cycles/step: split %.0f  propose %.0f  eval %.0f  accept %.0f  store %.0f\n", \
+    (double)ph_[0] / P.nsteps, (double)ph_[1] / P.nsteps, (double)ph_[2] / P.nsteps, (double)ph_[3] / P.nsteps, (double)ph_[4] / P.nsteps);
+#else
+#define PHASE_DECL
+#define PHASE_MARK(i)
+#define PHASE_PRINT
+#endif
 
 struct EnsembleParams {
   bisip_model_desc d;
@@ -28,6 +42,11 @@ struct EnsembleParams {
   const double* y; const double* yerr; const double* bounds;
   double* coords; double* lp; double* chain; double* logp;
   int* accepted; int* flags;
+  unsigned long long stagger_ns;   // start delay of every second CTA on an SM (0 = off)
+  // host-precomputed constants (kept in the parameter bank, not in registers)
+  uint32_t kmask;                  // 2^ceil(log2 W) - 1
+  int a_pow2;                      // a is a power of two: zr*zr/a == zr*zr*inv_a exactly
+  double inv_a;
 };
 
 struct SamplerSmem {
@@ -35,9 +54,10 @@ struct SamplerSmem {
   double* lp;      // [W]
   double* prop;    // [rows_pad][ndim]
   double* chi;     // [rows_pad]
-  double* fac;     // [rows_pad]  (ndim-1) ln zz
+  double* fac;     // [rows_pad]  stretch factor zz of the proposal
   double* bnd;     // [2][ndim]
   double* red;     // [kWarps]
+  long long* bkey; // [2][ndim] ordered-integer image of bnd (NaN bounds never match)
   uint32_t* keys;  // [W]
   int* list;       // [W]   walker at rank
   int* acc;        // [W]
@@ -48,9 +68,9 @@ __host__ __device__ inline int sampler_rows_pad(int W) { return ceil_div((W + 1)
 
 __host__ __device__ inline size_t sampler_smem_bytes(int W, int ndim) {
   const int rp = sampler_rows_pad(W);
-  size_t dbl = (size_t)W * ndim + W + (size_t)rp * ndim + rp + rp + 2 * ndim + kWarps;
-  size_t ints = (size_t)W * 3 + rp;
-  return dbl * 8 + ints * 4 + 16;
+  size_t dbl = (size_t)W * ndim + W + (size_t)rp * ndim + rp + rp + 4 * ndim + kWarps;
+  size_t ints = (size_t)W * 3 + 4 + rp;
+  return dbl * 8 + ints * 4 + 32;
 }
 
 __device__ inline void sampler_carve(SamplerSmem& s, double* base, int W, int ndim) {
@@ -62,8 +82,9 @@ __device__ inline void sampler_carve(SamplerSmem& s, double* base, int W, int nd
   s.fac = base; base += rp;
   s.bnd = base; base += 2 * ndim;
   s.red = base; base += kWarps;
-  s.keys = reinterpret_cast<uint32_t*>(base);
-  s.list = reinterpret_cast<int*>(s.keys + W);
+  s.bkey = reinterpret_cast<long long*>(base); base += 2 * ndim;
+  s.keys = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(base) + 15) & ~uintptr_t(15));   // LDS.128
+  s.list = reinterpret_cast<int*>(s.keys + ((W + 3) & ~3));
   s.acc = s.list + W;
   s.inb = s.acc + W;
 }
@@ -72,6 +93,23 @@ __device__ inline void sampler_carve(SamplerSmem& s, double* base, int W, int nd
 __device__ __forceinline__ bool in_bounds(const double* th, const double* bnd, int ndim) {
   bool ok = true;
   for (int d = 0; d < ndim; ++d) ok = ok && (bnd[d] < th[d]) && (th[d] < bnd[ndim + d]);
+  return ok;
+}
+
+// Same predicate on the integer pipe (FP64 compares would queue behind the other CTA's DMMA
+// stream): doubles mapped to int64 keys that order like IEEE numbers (-0 canonicalised to +0).
+// NaNs map beyond +/-inf, so `lo < x < hi` is false for them exactly as in IEEE arithmetic.
+__device__ __forceinline__ long long ordered_key(double x) {
+  long long b = __double_as_longlong(x);
+  if ((b << 1) == 0) b = 0;
+  return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
+}
+__device__ __forceinline__ bool in_bounds_keys(const double* th, const long long* bkey, int ndim) {
+  bool ok = true;
+  for (int d = 0; d < ndim; ++d) {
+    const long long k = ordered_key(th[d]);
+    ok = ok && (bkey[d] < k) && (k < bkey[ndim + d]);
+  }
   return ok;
 }
 
@@ -113,10 +151,39 @@ struct VecEvaluator {
   }
 };
 
+// Co-resident CTAs that start together stay phase-locked: both run their serial phases
+// (split, proposals, accept) at the same time and then fight for the math pipe at the same time.
+// The second CTA to arrive on an SM therefore starts a fraction of a step late, after which the two
+// alternate (one samples/accepts while the other owns the FP64 tensor pipe).  The arrival order
+// comes from a per-SM counter that is never reset (only its parity matters).
+__device__ unsigned int g_sm_arrivals[1024];
+
+__device__ __forceinline__ void stagger_start(unsigned long long delay_ns) {
+  __shared__ unsigned int slot_s;
+  if (threadIdx.x == 0) {
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    slot_s = atomicAdd(&g_sm_arrivals[smid & 1023], 1u);
+  }
+  __syncthreads();
+  if ((slot_s & 1u) && delay_ns) {
+    if (threadIdx.x == 0) {
+      unsigned long long t0, t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      do {
+        __nanosleep(1000);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      } while (t1 - t0 < delay_ns);
+    }
+    __syncthreads();
+  }
+}
+
 template <class Eval, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) ensemble_kernel(const EnsembleParams P) {
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x;
+  if (MINB > 1) stagger_start(P.stagger_ns);
   const int b = blockIdx.x;
   const int W = P.W, ndim = P.d.ndim;
   const int rows_pad = sampler_rows_pad(W);
@@ -128,7 +195,10 @@ __global__ void __launch_bounds__(kThreads, MINB) ensemble_kernel(const Ensemble
   sampler_carve(s, p, W, ndim);
 
   // ---- per-spectrum constants + initial ensemble ---------------------------------------
-  for (int i = tid; i < 2 * ndim; i += kThreads) s.bnd[i] = P.bounds[i];
+  for (int i = tid; i < 2 * ndim; i += kThreads) {
+    s.bnd[i] = P.bounds[i];
+    s.bkey[i] = ordered_key(P.bounds[i]);
+  }
   const double* gc = P.coords + (size_t)b * W * ndim;
   for (int i = tid; i < W * ndim; i += kThreads) s.coords[i] = gc[i];
   for (int i = tid; i < W; i += kThreads) s.acc[i] = 0;
@@ -157,28 +227,38 @@ __global__ void __launch_bounds__(kThreads, MINB) ensemble_kernel(const Ensemble
   const uint32_t k0 = (uint32_t)P.seed, k1 = (uint32_t)(P.seed >> 32);
   const uint32_t spec = P.spectrum0 + (uint32_t)b;
   const int first = P.discard + P.thin - 1;
-  const double am1 = P.a - 1.0, dm1 = (double)ndim - 1.0;
-  int kept = 0;
+    int kept = 0;
 
+  PHASE_DECL
   for (int it = 0; it < P.nsteps; ++it) {
     const uint32_t t = (uint32_t)(P.step0 + it);
+    PHASE_MARK(5)
     // ---- random equal split (emcee: shuffle(arange(W) % 2)) ------------------------------
-    for (int i = tid; i < W; i += kThreads) {
-      const u32x4 r = philox4x32_10((uint32_t)(i >> 2), t, spec, 0u, k0, k1);
-      const int sel = i & 3;
-      s.keys[i] = sel == 0 ? r.x : sel == 1 ? r.y : sel == 2 ? r.z : r.w;
+    const int Wpad4 = (W + 3) & ~3;
+    for (int i = tid; i < Wpad4; i += kThreads) {
+      uint32_t key = 0xffffffffu;                       // padding sorts last, never counted
+      if (i < W) {
+        const u32x4 r = philox4x32_10((uint32_t)(i >> 2), t, spec, 0u, k0, k1);
+        const int sel = i & 3;
+        const uint32_t word = sel == 0 ? r.x : sel == 1 ? r.y : sel == 2 ? r.z : r.w;
+        key = (word & ~P.kmask) | (uint32_t)i;
+      }
+      s.keys[i] = key;
     }
     __syncthreads();
     for (int i = tid; i < W; i += kThreads) {
       const uint32_t ki = s.keys[i];
+      const uint4* kv = reinterpret_cast<const uint4*>(s.keys);
       int rank = 0;
-      for (int j = 0; j < W; ++j) {
-        const uint32_t kj = s.keys[j];
-        rank += (kj < ki) || (kj == ki && j < i);
+#pragma unroll 4
+      for (int j = 0; j < Wpad4 / 4; ++j) {
+        const uint4 k4 = kv[j];
+        rank += (k4.x < ki) + (k4.y < ki) + (k4.z < ki) + (k4.w < ki);
       }
       s.list[rank] = i;
     }
     __syncthreads();
+    PHASE_MARK(0)
 
     for (int sp = 0; sp < 2; ++sp) {
       const int off = sp ? H0 : 0, Hs = sp ? W - H0 : H0;
@@ -187,36 +267,53 @@ __global__ void __launch_bounds__(kThreads, MINB) ensemble_kernel(const Ensemble
       for (int q = tid; q < Hs; q += kThreads) {
         const u32x4 r = philox4x32_10((uint32_t)q, t, spec, (uint32_t)(1 + 2 * sp), k0, k1);
         const double u = u53(r.x, r.y);
-        const double zr = __dadd_rn(__dmul_rn(am1, u), 1.0);
-        const double zz = __ddiv_rn(__dmul_rn(zr, zr), P.a);
+        const double zr = __dadd_rn(__dmul_rn(P.a - 1.0, u), 1.0);
+        const double zz = P.a_pow2 ? __dmul_rn(__dmul_rn(zr, zr), P.inv_a) : __ddiv_rn(__dmul_rn(zr, zr), P.a);
         const int j = s.list[coff + (int)__umulhi(r.z, (uint32_t)Nc)];
         const int k = s.list[off + q];
         const double* cj = s.coords + j * ndim;
         const double* sk = s.coords + k * ndim;
         double* dst = s.prop + q * ndim;
         for (int d = 0; d < ndim; ++d) dst[d] = __dsub_rn(cj[d], __dmul_rn(__dsub_rn(cj[d], sk[d]), zz));
-        s.fac[q] = __dmul_rn(dm1, log(zz));
-        s.inb[q] = in_bounds(dst, s.bnd, ndim) ? 1 : 0;
+        s.fac[q] = zz;
+        s.inb[q] = in_bounds_keys(dst, s.bkey, ndim) ? 1 : 0;
       }
       __syncthreads();
+      PHASE_MARK(1)
       // ---- fused forward + chi^2 for all proposals ------------------------------------------
       ev.eval_chi(s.prop, ndim, Hs, s.chi);
       __syncthreads();
+      PHASE_MARK(2)
       // ---- accept / reject ---------------------------------------------------------------------
       for (int q = tid; q < Hs; q += kThreads) {
         const u32x4 r = philox4x32_10((uint32_t)q, t, spec, (uint32_t)(2 + 2 * sp), k0, k1);
-        const double lu = log(u53(r.x, r.y));
+        const double u2 = u53(r.x, r.y);
         const int k = s.list[off + q];
         const double lpn = s.inb[q] ? -0.5 * (s.chi[q] + llc) : neg_inf();
         if (lpn != lpn) flag |= 1;
-        const double lnpdiff = __dsub_rn(__dadd_rn(s.fac[q], lpn), s.lp[k]);
-        if (lnpdiff > lu) {
+        // emcee: accept iff (ndim-1) ln zz + lp' - lp > ln u.  The two logarithms are first
+        // taken in FP32 (SFU/FMA pipes, |error| < 1e-5): unless the margin is below 1e-4 the FP64
+        // decision is already determined; otherwise (about 1 proposal in 10^4) it is recomputed in
+        // FP64 exactly as the oracle does.  Both paths give the decision of the FP64 formula.
+        const double dlp = __dsub_rn(lpn, s.lp[k]);
+        const double zz = s.fac[q];
+        const float lf = (float)(ndim - 1) * logf((float)zz) - logf((float)u2);
+        const double est = dlp + (double)lf;
+        bool accept;
+        if (fabs(est) > fma(1e-15, fabs(lpn) + fabs(s.lp[k]), 1e-4)) {   // margin >> FP32 + FP64 rounding
+          accept = est > 0.0;
+        } else {
+          const double lnpdiff = __dsub_rn(__dadd_rn(__dmul_rn((double)(ndim - 1), log(zz)), lpn), s.lp[k]);
+          accept = lnpdiff > log(u2);
+        }
+        if (accept) {
           for (int d = 0; d < ndim; ++d) s.coords[k * ndim + d] = s.prop[q * ndim + d];
           s.lp[k] = lpn;
           s.acc[k] += 1;
         }
       }
       __syncthreads();
+      PHASE_MARK(3)
     }
     // ---- backend.save_step: chain[it] = coords ; log_prob[it] = lp -----------------------------
     if (it >= first && (it - first) % P.thin == 0) {
@@ -230,7 +327,9 @@ __global__ void __launch_bounds__(kThreads, MINB) ensemble_kernel(const Ensemble
       }
       ++kept;
     }
+    PHASE_MARK(4)
   }
+  PHASE_PRINT
   // ---- final state ------------------------------------------------------------------------------
   double* gco = P.coords + (size_t)b * W * ndim;
   for (int i = tid; i < W * ndim; i += kThreads) gco[i] = s.coords[i];

@@ -207,8 +207,9 @@ static inline double u53(uint32_t a, uint32_t b) { /* NumPy legacy random_sample
  * Stretch-move ensemble sampler with the SAME Philox stream layout as the CUDA kernel
  * (bisip_b200/csrc/sampler.cuh), restating emcee's RedBlueMove/StretchMove:
  *   counter = (index, step, spectrum, purpose), key = (seed_lo, seed_hi)
- *   purpose 0: shuffle keys — walker i uses word (i&3) of counter index (i>>2); walkers are
- *              ranked by (key, i); ranks [0,H0) form split 0, [H0,W) split 1, H0=(W+1)/2
+ *   purpose 0: shuffle keys — walker i uses word (i&3) of counter index (i>>2) with its low
+ *              ceil(log2 W) bits replaced by i (unique keys); walkers are ranked by key;
+ *              ranks [0,H0) form split 0, [H0,W) split 1, H0=(W+1)/2
  *   purpose 1+2s: proposal p of split s: u=u53(x0,x1); partner = mulhi(x2, Nc)
  *   purpose 2+2s: proposal p of split s: accept draw u53(x0,x1)
  * chain (nkeep,W,ndim), logp (nkeep,W): steps t with t>=discard+thin-1 and
@@ -236,16 +237,19 @@ int oracle_ensemble_run(const oracle_problem *p, double *coords, int W, int nste
   }
   const int first = discard + thin - 1;
   int kept = 0;
+  uint32_t kmask = 1;
+  while ((int)kmask < W) kmask <<= 1;
+  kmask -= 1;
   for (int it = 0; it < nsteps; ++it) {
     const uint32_t t = (uint32_t)(step0 + it);
     for (int i = 0; i < W; ++i) {
       uint32_t ctr[4] = {(uint32_t)(i >> 2), t, spectrum, 0u}, out[4];
       oracle_philox4x32_10(ctr, key, out);
-      keys[i] = out[i & 3];
+      keys[i] = (out[i & 3] & ~kmask) | (uint32_t)i;   /* unique: low bits carry the walker index */
     }
     for (int i = 0; i < W; ++i) {
       int rank = 0;
-      for (int j = 0; j < W; ++j) rank += (keys[j] < keys[i]) || (keys[j] == keys[i] && j < i);
+      for (int j = 0; j < W; ++j) rank += keys[j] < keys[i];
       list[rank] = i;
     }
     for (int s = 0; s < 2; ++s) {
