@@ -50,7 +50,6 @@ int check_desc(const bisip_model_desc* d) {
       if (d->n_tau <= 0 || d->n_coef <= 0) return fail(BISIP_ERR_BAD_ARG, "Decomp n_tau/n_coef must be positive");
       if (d->ndim != 1 + d->n_coef) return fail(BISIP_ERR_BAD_ARG, "Decomp ndim != 1+n_coef");
       if (d->n_coef > 8) return fail(BISIP_ERR_UNSUPPORTED, "Decomp poly_deg > 7 not supported");
-      if (d->n_tau > 64) return fail(BISIP_ERR_UNSUPPORTED, "Decomp n_tau > 64 not supported yet");
       if (d->precision != BISIP_PREC_FP64) return fail(BISIP_ERR_UNSUPPORTED, "only FP64 precision is built");
       break;
     default:
@@ -165,8 +164,94 @@ int launch(K kernel, dim3 grid, size_t smem, cudaStream_t st, const char* name, 
   return BISIP_OK;
 }
 
+template <typename K>
+int launch_cluster(K kernel, dim3 grid, int cluster, size_t smem, cudaStream_t st, const char* name,
+                   const void* params_ptr) {
+  if ((int)smem > device_smem_optin())
+    return fail(BISIP_ERR_UNSUPPORTED, std::string(name) + ": problem does not fit in shared memory");
+  BISIP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  void* args[] = {const_cast<void*>(params_ptr)};
+  BISIP_CUDA(cudaLaunchKernelExC(&cfg, (const void*)kernel, args));
+  g_launches.fetch_add(1);
+  return BISIP_OK;
+}
+
+// Large tau grids: pick the cluster size (column split) so that K fits; prefer two CTAs per SM.
+struct RcPlan { int cs; bool two_per_sm; size_t smem; };
+int plan_rc(const bisip_model_desc& d, size_t other_bytes, int rows_pad, RcPlan* out) {
+  const size_t two = 113 * 1024, one = (size_t)device_smem_optin();
+  const int cands[3] = {1, 2, 4};
+  for (int pass = 0; pass < 2; ++pass)
+    for (int i = 0; i < 3; ++i) {
+      const size_t smem = other_bytes + DecompRCEvaluator::smem_doubles(d, rows_pad, cands[i]) * 8;
+      if (smem <= (pass == 0 ? two : one)) { *out = {cands[i], pass == 0, smem}; return BISIP_OK; }
+    }
+  return fail(BISIP_ERR_UNSUPPORTED, "Decomp: n_tau x n_freq too large for a 4-CTA cluster's shared memory");
+}
+
+// Batched forward / log-probability for large tau grids: grid (chunks*CS, B), cluster (CS,1,1).
+template <bool WANT_Z>
+__global__ void __launch_bounds__(kThreads) decomp_rc_batch_kernel(const BatchParams P) {
+  extern __shared__ __align__(16) double smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int cs = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
+  const int b = blockIdx.y, ndim = P.d.ndim, N = P.d.n_freq;
+  const int chunk0 = blockIdx.x / cs, nchunks = gridDim.x / cs;
+  DecompRCShape sh(P.d.n_freq, P.d.n_tau, P.d.n_coef, cs, crank);
+  DecompRCSmem s;
+  double* p = decomp_rc_carve(s, smem, sh, kRows);
+  double* prop = p; p += kRows * ndim;
+  double* chi = p; p += kRows;
+  double* bnd = p; p += 2 * ndim;
+  double* red = p;
+  if (!WANT_Z) for (int i = threadIdx.x; i < 2 * ndim; i += kThreads) bnd[i] = P.bounds[i];
+  decomp_rc_init(s, sh, P.d.c_exp, P.w + (size_t)b * P.w_stride, P.taus + (size_t)b * P.tau_stride,
+                 P.log_taus + (size_t)b * P.tau_stride * P.d.n_coef,
+                 WANT_Z ? nullptr : P.y + (size_t)b * 2 * N, WANT_Z ? nullptr : P.yerr + (size_t)b * 2 * N, red);
+  for (int r0 = chunk0 * kRows; r0 < P.n_theta; r0 += nchunks * kRows) {
+    const int n = min(kRows, P.n_theta - r0);
+    const double* th = P.theta + ((size_t)b * P.n_theta + r0) * ndim;
+    for (int i = threadIdx.x; i < kRows * ndim; i += kThreads) prop[i] = (i < n * ndim) ? th[i] : 0.0;
+    __syncthreads();
+    if (WANT_Z) {
+      decomp_rc_eval_Z(s, sh, prop, ndim, n, P.Z + ((size_t)b * P.n_theta + r0) * 2 * N);
+    } else {
+      decomp_rc_eval_chi(s, sh, prop, ndim, n, kRows, chi);
+      __syncthreads();
+      if (crank == 0)
+        for (int q = threadIdx.x; q < n; q += kThreads)
+          P.lp[(size_t)b * P.n_theta + r0 + q] =
+              in_bounds(prop + q * ndim, bnd, ndim) ? -0.5 * (chi[q] + s.llconst) : neg_inf();
+    }
+    __syncthreads();
+  }
+  if (cs > 1) cluster.sync();
+}
+
 template <bool WANT_Z>
 int run_batch(const BatchParams& P, cudaStream_t st) {
+  if (P.d.model == BISIP_MODEL_DECOMP && P.d.n_tau > 64) {
+    RcPlan plan;
+    const size_t other = ((size_t)kRows * P.d.ndim + kRows + 2 * P.d.ndim + kWarps) * 8;
+    if (int rc = plan_rc(P.d, other, kRows, &plan)) return rc;
+    int chunks = ceil_div(P.n_theta, kRows);
+    const int cap = max(1, (148 * 2) / max(1, P.B * plan.cs));
+    if (chunks > cap) chunks = cap;
+    return launch_cluster(decomp_rc_batch_kernel<WANT_Z>, dim3(chunks * plan.cs, P.B), plan.cs, plan.smem, st,
+                          "decomp_rc_batch", &P);
+  }
   const size_t smem = batch_smem_bytes(P.d);
   int chunks = ceil_div(P.n_theta, kRows);
   const int cap = max(1, (148 * 8) / max(1, P.B));   // enough CTAs to fill the chip, no more
@@ -293,6 +378,15 @@ int bisip_ensemble_run(const bisip_model_desc* desc, int n_spectra, int n_walker
       smem += VecEvaluator<ShinRow>::smem_doubles(*desc, rp) * 8;
       return launch(ensemble_kernel<VecEvaluator<ShinRow>, 2>, grid, smem, st, "ensemble_shin", &P);
     default: {
+      if (desc->n_tau > 64) {
+        RcPlan plan;
+        if (int rc = plan_rc(*desc, smem, rp, &plan)) return rc;
+        if ((long long)n_spectra * plan.cs > 2147483647LL) return fail(BISIP_ERR_UNSUPPORTED, "too many spectra per call");
+        dim3 g(n_spectra * plan.cs);
+        if (plan.two_per_sm)
+          return launch_cluster(ensemble_kernel<DecompRCEvaluator, 2>, g, plan.cs, plan.smem, st, "ensemble_decomp_rc", &P);
+        return launch_cluster(ensemble_kernel<DecompRCEvaluator, 1>, g, plan.cs, plan.smem, st, "ensemble_decomp_rc", &P);
+      }
       smem += DecompEvaluator<4>::smem_doubles(*desc, rp) * 8;
       const int KC = ceil_div(desc->n_tau, 16);
       switch (KC) {

@@ -13,6 +13,7 @@
 #pragma once
 #include "common.cuh"
 #include "decomp_eval.cuh"
+#include "decomp_rc.cuh"
 #include "models.cuh"
 
 namespace bisip {
@@ -116,10 +117,11 @@ __device__ __forceinline__ bool in_bounds_keys(const double* th, const long long
 // Evaluator adaptors -------------------------------------------------------------------
 template <int KC>
 struct DecompEvaluator {
+  static constexpr bool kClustered = false;
   DecompSmem sm;
   DecompShape sh;
   int rows_pad;
-  __device__ DecompEvaluator(const bisip_model_desc& d) : sh(d.n_freq, d.n_tau, d.n_coef) {}
+  __device__ DecompEvaluator(const bisip_model_desc& d, int, int) : sh(d.n_freq, d.n_tau, d.n_coef) {}
   static __host__ size_t smem_doubles(const bisip_model_desc& d, int rows_pad) {
     return decomp_smem_doubles(DecompShape(d.n_freq, d.n_tau, d.n_coef), rows_pad);
   }
@@ -134,11 +136,33 @@ struct DecompEvaluator {
   }
 };
 
+// Large tau grids: stage 1 recomputed per k chunk, frequency columns split over a CTA cluster.
+struct DecompRCEvaluator {
+  static constexpr bool kClustered = true;
+  DecompRCSmem sm;
+  DecompRCShape sh;
+  int rows_pad;
+  __device__ DecompRCEvaluator(const bisip_model_desc& d, int cs, int rank) : sh(d.n_freq, d.n_tau, d.n_coef, cs, rank) {}
+  static __host__ size_t smem_doubles(const bisip_model_desc& d, int rows_pad, int cs) {
+    return decomp_rc_smem_doubles(DecompRCShape(d.n_freq, d.n_tau, d.n_coef, cs, 0), rows_pad);
+  }
+  __device__ double* carve(double* base, int rp) { rows_pad = rp; return decomp_rc_carve(sm, base, sh, rp); }
+  __device__ void init(const bisip_model_desc& d, const double* w, const double* taus, const double* log_taus,
+                       const double* y, const double* yerr, double* red) {
+    decomp_rc_init(sm, sh, d.c_exp, w, taus, log_taus, y, yerr, red);
+  }
+  __device__ double llconst() const { return sm.llconst; }
+  __device__ void eval_chi(const double* prop, int ndim, int nrows, double* chi) {
+    decomp_rc_eval_chi(sm, sh, prop, ndim, nrows, rows_pad, chi);
+  }
+};
+
 template <class Row>
 struct VecEvaluator {
+  static constexpr bool kClustered = false;
   VecSmem sm;
   int N, n_modes;
-  __device__ VecEvaluator(const bisip_model_desc& d) : N(d.n_freq), n_modes(d.n_modes) {}
+  __device__ VecEvaluator(const bisip_model_desc& d, int, int) : N(d.n_freq), n_modes(d.n_modes) {}
   static __host__ size_t smem_doubles(const bisip_model_desc& d, int) { return vec_smem_doubles(d.n_freq); }
   __device__ double* carve(double* base, int) { return vec_carve(sm, base, N); }
   __device__ void init(const bisip_model_desc&, const double* w, const double*, const double*, const double* y,
@@ -183,13 +207,22 @@ template <class Eval, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) ensemble_kernel(const EnsembleParams P) {
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x;
-  if (MINB > 1) stagger_start(P.stagger_ns);
-  const int b = blockIdx.x;
+  if (MINB > 1 && !Eval::kClustered) stagger_start(P.stagger_ns);
+  // clustered evaluators: the CTAs of a cluster own one spectrum together (column split); all of
+  // them run the sampler on identical state, rank 0 alone writes the results
+  int cs = 1, crank = 0;
+  if (Eval::kClustered) {
+    cg::cluster_group cluster = cg::this_cluster();
+    cs = (int)cluster.num_blocks();
+    crank = (int)cluster.block_rank();
+  }
+  const int b = blockIdx.x / cs;
+  const bool writer = (crank == 0);
   const int W = P.W, ndim = P.d.ndim;
   const int rows_pad = sampler_rows_pad(W);
   const int H0 = (W + 1) / 2;
 
-  Eval ev(P.d);
+  Eval ev(P.d, cs, crank);
   SamplerSmem s;
   double* p = ev.carve(smem, rows_pad);
   sampler_carve(s, p, W, ndim);
@@ -317,11 +350,11 @@ __global__ void __launch_bounds__(kThreads, MINB) ensemble_kernel(const Ensemble
     }
     // ---- backend.save_step: chain[it] = coords ; log_prob[it] = lp -----------------------------
     if (it >= first && (it - first) % P.thin == 0) {
-      if (P.chain != nullptr) {
+      if (P.chain != nullptr && writer) {
         double* dst = P.chain + ((size_t)b * P.nkeep + kept) * W * ndim;
         for (int i = tid; i < W * ndim; i += kThreads) __stcs(dst + i, s.coords[i]);
       }
-      if (P.logp != nullptr) {
+      if (P.logp != nullptr && writer) {
         double* dst = P.logp + ((size_t)b * P.nkeep + kept) * W;
         for (int i = tid; i < W; i += kThreads) __stcs(dst + i, s.lp[i]);
       }
@@ -331,13 +364,16 @@ __global__ void __launch_bounds__(kThreads, MINB) ensemble_kernel(const Ensemble
   }
   PHASE_PRINT
   // ---- final state ------------------------------------------------------------------------------
-  double* gco = P.coords + (size_t)b * W * ndim;
-  for (int i = tid; i < W * ndim; i += kThreads) gco[i] = s.coords[i];
-  for (int i = tid; i < W; i += kThreads) {
-    if (P.lp) P.lp[(size_t)b * W + i] = s.lp[i];
-    if (P.accepted) P.accepted[(size_t)b * W + i] = s.acc[i];
+  if (writer) {
+    double* gco = P.coords + (size_t)b * W * ndim;
+    for (int i = tid; i < W * ndim; i += kThreads) gco[i] = s.coords[i];
+    for (int i = tid; i < W; i += kThreads) {
+      if (P.lp) P.lp[(size_t)b * W + i] = s.lp[i];
+      if (P.accepted) P.accepted[(size_t)b * W + i] = s.acc[i];
+    }
+    if (P.flags && flag) atomicOr(P.flags + b, flag);
   }
-  if (P.flags && flag) atomicOr(P.flags + b, flag);
+  if (Eval::kClustered && cs > 1) cg::this_cluster().sync();   // peers may still read our shared memory
 }
 
 }  // namespace bisip

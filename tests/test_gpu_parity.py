@@ -85,7 +85,7 @@ def test_raw_kernels_other_frequencies(gold_fl, data_files):
         assert normwise(got[None], gold_fl[f'raw/{key}'][None]).max() <= TOL
 
 
-SYN = ['syn_decomp_s64', 'syn_colecole', 'syn_dias', 'syn_shin']
+SYN = ['syn_decomp_s64', 'syn_decomp_s128', 'syn_decomp_s256', 'syn_colecole', 'syn_dias', 'syn_shin']
 
 
 @pytest.mark.parametrize("tag", SYN)
@@ -96,7 +96,7 @@ def test_synthetic_batch_logprob(tag, gold_fl):
     from bisip_b200.batch import BatchInversion
     model = tag.split('_')[1]
     _, w = synthetic.frequencies(64)
-    kw = dict(poly_deg=4, n_tau=64) if model == 'decomp' else {}
+    kw = dict(poly_deg=4, n_tau=int(tag.split('_s')[1]), c_exp=float(gold_fl[f'{tag}/c_exp'])) if model == 'decomp' else {}
     inv = BatchInversion(model, w, gold_fl[f'{tag}/zn'], gold_fl[f'{tag}/zn_err'], **kw)
     dev = inv.device
     th = gold_fl[f'{tag}/theta']

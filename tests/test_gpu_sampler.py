@@ -41,6 +41,41 @@ def test_chain_matches_oracle_same_stream(case, W, T, gold_fl, gold_ld, data_fil
     assert np.max(np.abs(lp[fin] - ref['log_prob'][fin]) / np.maximum(1, np.abs(ref['log_prob'][fin]))) <= 1e-12
 
 
+@pytest.mark.parametrize("tag,W,T", [('syn_decomp_s128', 64, 40), ('syn_decomp_s256', 256, 12), ('syn_decomp_s128', 33, 30)])
+def test_large_tau_grid_chain_matches_oracle(tag, W, T, gold_fl):
+    """n_tau > 64: stage-1 recompute + column split over a CTA cluster (DSMEM exchange of partial
+    chi^2).  Same Philox stream as the oracle => identical chain."""
+    from bisip_b200 import synthetic
+    from bisip_b200.batch import BatchInversion
+    from oracle import oracle
+    _, w = synthetic.frequencies(64)
+    S, c_exp = int(tag.split('_s')[1]), float(gold_fl[f'{tag}/c_exp'])
+    zn, ze, bounds = gold_fl[f'{tag}/zn'], gold_fl[f'{tag}/zn_err'], gold_fl[f'{tag}/bounds']
+    inv = BatchInversion('decomp', w, zn, ze, nwalkers=W, nsteps=T, poly_deg=4, n_tau=S, c_exp=c_exp, seed=77)
+    p0 = inv.draw_p0(0, 4)
+    res = inv.fit(p0=p0, keep_chain=True)
+    for b in (0, 3):
+        prob = oracle.Problem('decomp', w, zn[b], ze[b], bounds, taus=gold_fl[f'{tag}/taus'],
+                              log_taus=gold_fl[f'{tag}/log_taus'], c_exp=c_exp)
+        ref = prob.run(p0[b], T, seed=77, spectrum=b)
+        np.testing.assert_array_equal(res['chain'][b], ref['chain'])
+        fin = np.isfinite(ref['log_prob'])
+        assert np.max(np.abs(res['log_prob'][b][fin] - ref['log_prob'][fin]) / np.maximum(1, np.abs(ref['log_prob'][fin]))) <= 1e-12
+
+
+def test_reference_default_tau_grid_n64(gold_fl):
+    """The reference hard-codes n_tau = 2N (models.py:203): 128 taus for a 64-frequency spectrum."""
+    from bisip_b200 import synthetic
+    from bisip_b200.batch import BatchInversion
+    _, w = synthetic.frequencies(64)
+    inv = BatchInversion('decomp', w, gold_fl['syn_decomp_s128/zn'], gold_fl['syn_decomp_s128/zn_err'], nwalkers=32,
+                         nsteps=20, poly_deg=4)
+    assert inv.taus.shape == (128,)
+    np.testing.assert_array_equal(inv.taus, gold_fl['syn_decomp_s128/taus'])
+    r = inv.fit()
+    assert np.all(r['flags'] == 0) and np.all(np.isfinite(r['mean']))
+
+
 def test_logp_consistent_with_chain(gold_fl, data_files):
     """Stored log-probabilities equal the log-probability recomputed at the stored positions."""
     m, _ = _gpu_run('decomp_p4_debye', gold_fl, data_files, 64, 300, 5)
