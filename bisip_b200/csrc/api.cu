@@ -50,7 +50,8 @@ int check_desc(const bisip_model_desc* d) {
       if (d->n_tau <= 0 || d->n_coef <= 0) return fail(BISIP_ERR_BAD_ARG, "Decomp n_tau/n_coef must be positive");
       if (d->ndim != 1 + d->n_coef) return fail(BISIP_ERR_BAD_ARG, "Decomp ndim != 1+n_coef");
       if (d->n_coef > 8) return fail(BISIP_ERR_UNSUPPORTED, "Decomp poly_deg > 7 not supported");
-      if (d->precision != BISIP_PREC_FP64) return fail(BISIP_ERR_UNSUPPORTED, "only FP64 precision is built");
+      if (d->precision != BISIP_PREC_FP64 && d->precision != BISIP_PREC_TF32 && d->precision != BISIP_PREC_3XTF32)
+        return fail(BISIP_ERR_BAD_ARG, "unknown precision");
       break;
     default:
       return fail(BISIP_ERR_BAD_ARG, "unknown model id");
@@ -190,34 +191,70 @@ int launch_cluster(K kernel, dim3 grid, int cluster, size_t smem, cudaStream_t s
 
 // Large tau grids: pick the cluster size (column split) so that K fits; prefer two CTAs per SM.
 struct RcPlan { int cs; bool two_per_sm; size_t smem; };
+size_t rc_eval_doubles(const bisip_model_desc& d, int rows_pad, int cs) {
+  switch (d.precision) {
+    case BISIP_PREC_TF32: return DecompTF32Evaluator<1>::smem_doubles(d, rows_pad, cs);
+    case BISIP_PREC_3XTF32: return DecompTF32Evaluator<3>::smem_doubles(d, rows_pad, cs);
+    default: return DecompRCEvaluator::smem_doubles(d, rows_pad, cs);
+  }
+}
 int plan_rc(const bisip_model_desc& d, size_t other_bytes, int rows_pad, RcPlan* out) {
   const size_t two = 113 * 1024, one = (size_t)device_smem_optin();
   const int cands[3] = {1, 2, 4};
   for (int pass = 0; pass < 2; ++pass)
     for (int i = 0; i < 3; ++i) {
-      const size_t smem = other_bytes + DecompRCEvaluator::smem_doubles(d, rows_pad, cands[i]) * 8;
+      const size_t smem = other_bytes + rc_eval_doubles(d, rows_pad, cands[i]) * 8;
       if (smem <= (pass == 0 ? two : one)) { *out = {cands[i], pass == 0, smem}; return BISIP_OK; }
     }
   return fail(BISIP_ERR_UNSUPPORTED, "Decomp: n_tau x n_freq too large for a 4-CTA cluster's shared memory");
 }
+// the clustered ("rc") layout serves every reduced-precision run and every FP64 run with n_tau > 64
+bool use_rc(const bisip_model_desc& d) {
+  return d.model == BISIP_MODEL_DECOMP && (d.n_tau > 64 || d.precision != BISIP_PREC_FP64);
+}
+
+// uniform access to the three clustered evaluators for the batch kernel
+template <int PREC> struct RcOps;
+template <> struct RcOps<0> {
+  using Smem = DecompRCSmem;
+  static __device__ double* carve(Smem& s, double* b, const DecompRCShape& sh, int rp) { return decomp_rc_carve(s, b, sh, rp); }
+  template <class... A> static __device__ void init(A&&... a) { decomp_rc_init(a...); }
+  template <class... A> static __device__ void chi(A&&... a) { decomp_rc_eval_chi(a...); }
+  template <class... A> static __device__ void Z(A&&... a) { decomp_rc_eval_Z(a...); }
+};
+template <> struct RcOps<1> {
+  using Smem = DecompTF32Smem;
+  static __device__ double* carve(Smem& s, double* b, const DecompRCShape& sh, int rp) { return decomp_tf32_carve<1>(s, b, sh, rp); }
+  template <class... A> static __device__ void init(A&&... a) { decomp_tf32_init<1>(a...); }
+  template <class... A> static __device__ void chi(A&&... a) { decomp_tf32_eval_chi<1>(a...); }
+  template <class... A> static __device__ void Z(A&&... a) { decomp_tf32_eval_Z<1>(a...); }
+};
+template <> struct RcOps<3> {
+  using Smem = DecompTF32Smem;
+  static __device__ double* carve(Smem& s, double* b, const DecompRCShape& sh, int rp) { return decomp_tf32_carve<3>(s, b, sh, rp); }
+  template <class... A> static __device__ void init(A&&... a) { decomp_tf32_init<3>(a...); }
+  template <class... A> static __device__ void chi(A&&... a) { decomp_tf32_eval_chi<3>(a...); }
+  template <class... A> static __device__ void Z(A&&... a) { decomp_tf32_eval_Z<3>(a...); }
+};
 
 // Batched forward / log-probability for large tau grids: grid (chunks*CS, B), cluster (CS,1,1).
-template <bool WANT_Z>
+template <int PREC, bool WANT_Z>
 __global__ void __launch_bounds__(kThreads) decomp_rc_batch_kernel(const BatchParams P) {
+  using Ops = RcOps<PREC>;
   extern __shared__ __align__(16) double smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const int cs = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
   const int b = blockIdx.y, ndim = P.d.ndim, N = P.d.n_freq;
   const int chunk0 = blockIdx.x / cs, nchunks = gridDim.x / cs;
   DecompRCShape sh(P.d.n_freq, P.d.n_tau, P.d.n_coef, cs, crank);
-  DecompRCSmem s;
-  double* p = decomp_rc_carve(s, smem, sh, kRows);
+  typename Ops::Smem s;
+  double* p = Ops::carve(s, smem, sh, kRows);
   double* prop = p; p += kRows * ndim;
   double* chi = p; p += kRows;
   double* bnd = p; p += 2 * ndim;
   double* red = p;
   if (!WANT_Z) for (int i = threadIdx.x; i < 2 * ndim; i += kThreads) bnd[i] = P.bounds[i];
-  decomp_rc_init(s, sh, P.d.c_exp, P.w + (size_t)b * P.w_stride, P.taus + (size_t)b * P.tau_stride,
+  Ops::init(s, sh, P.d.c_exp, P.w + (size_t)b * P.w_stride, P.taus + (size_t)b * P.tau_stride,
                  P.log_taus + (size_t)b * P.tau_stride * P.d.n_coef,
                  WANT_Z ? nullptr : P.y + (size_t)b * 2 * N, WANT_Z ? nullptr : P.yerr + (size_t)b * 2 * N, red);
   for (int r0 = chunk0 * kRows; r0 < P.n_theta; r0 += nchunks * kRows) {
@@ -226,9 +263,10 @@ __global__ void __launch_bounds__(kThreads) decomp_rc_batch_kernel(const BatchPa
     for (int i = threadIdx.x; i < kRows * ndim; i += kThreads) prop[i] = (i < n * ndim) ? th[i] : 0.0;
     __syncthreads();
     if (WANT_Z) {
-      decomp_rc_eval_Z(s, sh, prop, ndim, n, P.Z + ((size_t)b * P.n_theta + r0) * 2 * N);
+      Ops::Z(s, sh, prop, ndim, n, P.Z + ((size_t)b * P.n_theta + r0) * 2 * N);
     } else {
-      decomp_rc_eval_chi(s, sh, prop, ndim, n, kRows, chi);
+      const int rows_cap = kRows;
+      Ops::chi(s, sh, prop, ndim, n, rows_cap, chi);
       __syncthreads();
       if (crank == 0)
         for (int q = threadIdx.x; q < n; q += kThreads)
@@ -242,15 +280,19 @@ __global__ void __launch_bounds__(kThreads) decomp_rc_batch_kernel(const BatchPa
 
 template <bool WANT_Z>
 int run_batch(const BatchParams& P, cudaStream_t st) {
-  if (P.d.model == BISIP_MODEL_DECOMP && P.d.n_tau > 64) {
+  if (use_rc(P.d)) {
     RcPlan plan;
     const size_t other = ((size_t)kRows * P.d.ndim + kRows + 2 * P.d.ndim + kWarps) * 8;
     if (int rc = plan_rc(P.d, other, kRows, &plan)) return rc;
     int chunks = ceil_div(P.n_theta, kRows);
     const int cap = max(1, (148 * 2) / max(1, P.B * plan.cs));
     if (chunks > cap) chunks = cap;
-    return launch_cluster(decomp_rc_batch_kernel<WANT_Z>, dim3(chunks * plan.cs, P.B), plan.cs, plan.smem, st,
-                          "decomp_rc_batch", &P);
+    const dim3 g(chunks * plan.cs, P.B);
+    switch (P.d.precision) {
+      case BISIP_PREC_TF32: return launch_cluster(decomp_rc_batch_kernel<1, WANT_Z>, g, plan.cs, plan.smem, st, "decomp_tf32_batch", &P);
+      case BISIP_PREC_3XTF32: return launch_cluster(decomp_rc_batch_kernel<3, WANT_Z>, g, plan.cs, plan.smem, st, "decomp_3xtf32_batch", &P);
+      default: return launch_cluster(decomp_rc_batch_kernel<0, WANT_Z>, g, plan.cs, plan.smem, st, "decomp_rc_batch", &P);
+    }
   }
   const size_t smem = batch_smem_bytes(P.d);
   int chunks = ceil_div(P.n_theta, kRows);
@@ -378,14 +420,20 @@ int bisip_ensemble_run(const bisip_model_desc* desc, int n_spectra, int n_walker
       smem += VecEvaluator<ShinRow>::smem_doubles(*desc, rp) * 8;
       return launch(ensemble_kernel<VecEvaluator<ShinRow>, 2>, grid, smem, st, "ensemble_shin", &P);
     default: {
-      if (desc->n_tau > 64) {
+      if (use_rc(*desc)) {
         RcPlan plan;
         if (int rc = plan_rc(*desc, smem, rp, &plan)) return rc;
         if ((long long)n_spectra * plan.cs > 2147483647LL) return fail(BISIP_ERR_UNSUPPORTED, "too many spectra per call");
         dim3 g(n_spectra * plan.cs);
-        if (plan.two_per_sm)
-          return launch_cluster(ensemble_kernel<DecompRCEvaluator, 2>, g, plan.cs, plan.smem, st, "ensemble_decomp_rc", &P);
-        return launch_cluster(ensemble_kernel<DecompRCEvaluator, 1>, g, plan.cs, plan.smem, st, "ensemble_decomp_rc", &P);
+#define BISIP_RC_LAUNCH(EVAL, NAME)                                                                       \
+  return plan.two_per_sm ? launch_cluster(ensemble_kernel<EVAL, 2>, g, plan.cs, plan.smem, st, NAME, &P)  \
+                         : launch_cluster(ensemble_kernel<EVAL, 1>, g, plan.cs, plan.smem, st, NAME, &P)
+        switch (desc->precision) {
+          case BISIP_PREC_TF32: BISIP_RC_LAUNCH(DecompTF32Evaluator<1>, "ensemble_decomp_tf32");
+          case BISIP_PREC_3XTF32: BISIP_RC_LAUNCH(DecompTF32Evaluator<3>, "ensemble_decomp_3xtf32");
+          default: BISIP_RC_LAUNCH(DecompRCEvaluator, "ensemble_decomp_rc");
+        }
+#undef BISIP_RC_LAUNCH
       }
       smem += DecompEvaluator<4>::smem_doubles(*desc, rp) * 8;
       const int KC = ceil_div(desc->n_tau, 16);

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "decomp_eval.cuh"
 #include "decomp_rc.cuh"
+#include "decomp_tf32.cuh"
 #include "models.cuh"
 
 namespace bisip {
@@ -154,6 +155,28 @@ struct DecompRCEvaluator {
   __device__ double llconst() const { return sm.llconst; }
   __device__ void eval_chi(const double* prop, int ndim, int nrows, double* chi) {
     decomp_rc_eval_chi(sm, sh, prop, ndim, nrows, rows_pad, chi);
+  }
+};
+
+// TF32 (PREC=1) / 3xTF32 (PREC=3) stage 2, FP64 stage 1; same clustered work split.
+template <int PREC>
+struct DecompTF32Evaluator {
+  static constexpr bool kClustered = true;
+  DecompTF32Smem sm;
+  DecompRCShape sh;
+  int rows_pad;
+  __device__ DecompTF32Evaluator(const bisip_model_desc& d, int cs, int rank) : sh(d.n_freq, d.n_tau, d.n_coef, cs, rank) {}
+  static __host__ size_t smem_doubles(const bisip_model_desc& d, int rows_pad, int cs) {
+    return decomp_tf32_smem_doubles(DecompRCShape(d.n_freq, d.n_tau, d.n_coef, cs, 0), rows_pad, PREC);
+  }
+  __device__ double* carve(double* base, int rp) { rows_pad = rp; return decomp_tf32_carve<PREC>(sm, base, sh, rp); }
+  __device__ void init(const bisip_model_desc& d, const double* w, const double* taus, const double* log_taus,
+                       const double* y, const double* yerr, double* red) {
+    decomp_tf32_init<PREC>(sm, sh, d.c_exp, w, taus, log_taus, y, yerr, red);
+  }
+  __device__ double llconst() const { return sm.llconst; }
+  __device__ void eval_chi(const double* prop, int ndim, int nrows, double* chi) {
+    decomp_tf32_eval_chi<PREC>(sm, sh, prop, ndim, nrows, rows_pad, chi);
   }
 };
 

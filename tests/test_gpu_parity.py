@@ -126,3 +126,43 @@ def test_decomp_kernel_matrix(gold_fl, gold_ld):
         N = len(w)
         assert np.max(np.abs(K[:, :N] - ref.real)) <= 1e-14
         assert np.max(np.abs(K[:, N:] - ref.imag)) <= 1e-14
+
+
+@pytest.mark.parametrize("tag", ['syn_decomp_s64', 'syn_decomp_s128', 'syn_decomp_s256'])
+@pytest.mark.parametrize("prec,ztol,lptol", [('tf32', 1e-3, 3e-3), ('3xtf32', 2e-5, 5e-5)])
+def test_reduced_precision_within_stated_tolerance(tag, prec, ztol, lptol, gold_fl):
+    """TF32 / 3xTF32 stage 2 (FP64 stage 1, FP32 accumulate) against the reference golden values.
+    Stated tolerances (measured in profiles/r01_tf32_study.md, with head-room):
+      forward  max|dZ|/max|Z| <= 1e-3 (tf32), 2e-5 (3xtf32);  log-prob relative <= 3e-3 / 5e-5."""
+    from bisip_b200 import _lib, engine, synthetic
+    from bisip_b200.batch import BatchInversion
+    _, w = synthetic.frequencies(64)
+    inv = BatchInversion('decomp', w, gold_fl[f'{tag}/zn'], gold_fl[f'{tag}/zn_err'], poly_deg=4,
+                         n_tau=int(tag.split('_s')[1]), c_exp=float(gold_fl[f'{tag}/c_exp']), precision=prec)
+    dev = inv.device
+    th = gold_fl[f'{tag}/theta']
+    thb = _lib.dev_f64(np.broadcast_to(th, (4,) + th.shape).copy(), dev)
+    Z = engine.forward(inv._spec(), thb, _lib.dev_f64(w, dev)).cpu().numpy()
+    err = normwise(Z[0], gold_fl[f'{tag}/Z']).max()
+    assert 1e-9 < err <= ztol          # > 1e-9: really the reduced-precision path, not FP64
+    lp = engine.log_probability(inv._spec(), thb, _lib.dev_f64(w, dev), _lib.dev_f64(gold_fl[f'{tag}/zn'], dev),
+                                _lib.dev_f64(gold_fl[f'{tag}/zn_err'], dev), _lib.dev_f64(gold_fl[f'{tag}/bounds'], dev)).cpu().numpy()
+    ref = gold_fl[f'{tag}/lp']
+    assert np.array_equal(np.isneginf(lp), np.isneginf(ref))
+    assert lp_err(lp, ref).max() <= lptol
+
+
+def test_3xtf32_sampler_runs_and_agrees_statistically(gold_fl):
+    from bisip_b200 import synthetic
+    from bisip_b200.batch import BatchInversion
+    _, w = synthetic.frequencies(64)
+    tag = 'syn_decomp_s64'
+    out = {}
+    for prec in ('fp64', '3xtf32'):
+        inv = BatchInversion('decomp', w, gold_fl[f'{tag}/zn'], gold_fl[f'{tag}/zn_err'], nwalkers=64, nsteps=1500,
+                             poly_deg=4, n_tau=64, precision=prec, seed=3)
+        out[prec] = inv.fit(discard=750, thin=3)
+        assert np.all(out[prec]['flags'] == 0)
+    shift = np.abs(out['3xtf32']['percentiles'][:, 1] - out['fp64']['percentiles'][:, 1]) / out['fp64']['std']
+    assert shift.max() < 0.5             # medians agree within Monte-Carlo error
+    assert np.abs(out['3xtf32']['acceptance_fraction'] - out['fp64']['acceptance_fraction']).max() < 0.03
