@@ -300,7 +300,14 @@ int run_batch(const BatchParams& P, cudaStream_t st) {
   if (chunks > cap) chunks = cap;
   dim3 grid(chunks, P.B);
   switch (P.d.model) {
-    case BISIP_MODEL_COLECOLE: return launch(vec_batch_kernel<ColeColeRow, WANT_Z>, grid, smem, st, "colecole_batch", &P);
+    case BISIP_MODEL_COLECOLE:
+      switch (P.d.n_modes) {
+        case 1: return launch(vec_batch_kernel<ColeColeRowT<1>, WANT_Z>, grid, smem, st, "colecole_batch", &P);
+        case 2: return launch(vec_batch_kernel<ColeColeRowT<2>, WANT_Z>, grid, smem, st, "colecole_batch", &P);
+        case 3: return launch(vec_batch_kernel<ColeColeRowT<3>, WANT_Z>, grid, smem, st, "colecole_batch", &P);
+        case 4: return launch(vec_batch_kernel<ColeColeRowT<4>, WANT_Z>, grid, smem, st, "colecole_batch", &P);
+        default: return launch(vec_batch_kernel<ColeColeRow, WANT_Z>, grid, smem, st, "colecole_batch", &P);
+      }
     case BISIP_MODEL_DIAS: return launch(vec_batch_kernel<DiasRow, WANT_Z>, grid, smem, st, "dias_batch", &P);
     case BISIP_MODEL_SHIN: return launch(vec_batch_kernel<ShinRow, WANT_Z>, grid, smem, st, "shin_batch", &P);
     default: {
@@ -412,7 +419,13 @@ int bisip_ensemble_run(const bisip_model_desc* desc, int n_spectra, int n_walker
   switch (desc->model) {
     case BISIP_MODEL_COLECOLE:
       smem += VecEvaluator<ColeColeRow>::smem_doubles(*desc, rp) * 8;
-      return launch(ensemble_kernel<VecEvaluator<ColeColeRow>, 1>, grid, smem, st, "ensemble_colecole", &P);
+      switch (desc->n_modes) {
+        case 1: return launch(ensemble_kernel<VecEvaluator<ColeColeRowT<1>>, 2>, grid, smem, st, "ensemble_colecole", &P);
+        case 2: return launch(ensemble_kernel<VecEvaluator<ColeColeRowT<2>>, 2>, grid, smem, st, "ensemble_colecole", &P);
+        case 3: return launch(ensemble_kernel<VecEvaluator<ColeColeRowT<3>>, 2>, grid, smem, st, "ensemble_colecole", &P);
+        case 4: return launch(ensemble_kernel<VecEvaluator<ColeColeRowT<4>>, 1>, grid, smem, st, "ensemble_colecole", &P);
+        default: return launch(ensemble_kernel<VecEvaluator<ColeColeRow>, 1>, grid, smem, st, "ensemble_colecole", &P);
+      }
     case BISIP_MODEL_DIAS:
       smem += VecEvaluator<DiasRow>::smem_doubles(*desc, rp) * 8;
       return launch(ensemble_kernel<VecEvaluator<DiasRow>, 2>, grid, smem, st, "ensemble_dias", &P);
