@@ -104,7 +104,8 @@ __global__ void __launch_bounds__(kThreads) decomp_batch_kernel(const BatchParam
     if (WANT_Z) {
       decomp_eval_Z<KC>(s, sh, prop, ndim, n, P.Z + ((size_t)b * P.n_theta + r0) * 2 * N);
     } else {
-      decomp_eval_chi<KC>(s, sh, prop, ndim, n, kRows, chi);
+      NoSide ns;
+      decomp_eval_chi<KC>(s, sh, prop, ndim, n, kRows, chi, ns);
       __syncthreads();
       for (int q = threadIdx.x; q < n; q += kThreads)
         P.lp[(size_t)b * P.n_theta + r0 + q] =

@@ -178,17 +178,32 @@ __device__ __forceinline__ void decomp_stage2_tile(const DecompSmem& s, int nt, 
 // (likelihood mode of decomp_init: pre-scaled K, accumulators start at the data term).
 // Block-level; prop must be visible; on return chi[] is written but NOT yet synchronised
 // when NG==1, synchronised internally when the column tiles were split over warps.
-template <int KC>
-__device__ inline void decomp_eval_chi(const DecompSmem& s, const DecompShape& sh, const double* __restrict__ prop,
-                                       int ndim, int nrows, int rows_pad, double* chi) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, t = lane & 3;
-  const int RT = (nrows + 15) >> 4;
-  int NG = kWarps / RT;
+// How the (row tile, column group) work items are laid out for `nrows` proposals.
+__device__ __forceinline__ void decomp_work_split(const DecompShape& sh, int nrows, int& RT, int& NG, int& TPG) {
+  RT = (nrows + 15) >> 4;
+  NG = kWarps / RT;
   if (NG < 1) NG = 1;
   if (NG > sh.NT2) NG = sh.NT2;
-  const int TPG = ceil_div(sh.NT2, NG);
+  TPG = ceil_div(sh.NT2, NG);
   NG = ceil_div(sh.NT2, TPG);
+}
+// Column-tile iterations each warp executes in one evaluation (pacing of the interleaved side work).
+__device__ __forceinline__ int decomp_iters_per_warp(const DecompShape& sh, int nrows) {
+  int RT, NG, TPG;
+  decomp_work_split(sh, nrows, RT, NG, TPG);
+  return ceil_div(RT * NG, kWarps) * TPG;
+}
+struct NoSide {
+  __device__ __forceinline__ void advance() {}
+};
+
+template <int KC, class Side>
+__device__ inline void decomp_eval_chi(const DecompSmem& s, const DecompShape& sh, const double* __restrict__ prop,
+                                       int ndim, int nrows, int rows_pad, double* chi, Side& side) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  int RT, NG, TPG;
+  decomp_work_split(sh, nrows, RT, NG, TPG);
   for (int item = warp; item < RT * NG; item += kWarps) {
     const int r = item % RT, cg = item / RT;
     double A[KC][8];
@@ -211,6 +226,7 @@ __device__ inline void decomp_eval_chi(const DecompSmem& s, const DecompShape& s
         c[3] = fma(-R0b, ds.y, ys.y);
       }
       decomp_stage2_tile<KC>(s, nt, lane, A, c);      // c = (y - Z)/sigma
+      side.advance();                                  // integer side work rides along with the tiles
       chi0 = fma(c[0], c[0], chi0);
       chi0 = fma(c[1], c[1], chi0);
       chi1 = fma(c[2], c[2], chi1);

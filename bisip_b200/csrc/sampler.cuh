@@ -22,11 +22,16 @@ namespace bisip {
 // Developer build (-DBISIP_PHASE_TIMING, `make dbg`): block 0 accumulates SM cycles per phase and
 // prints them at the end.  Compiled out of the product library.
 #ifdef BISIP_PHASE_TIMING
-#define PHASE_DECL long long ph_[6] = {0, 0, 0, 0, 0, 0}; long long ph_t_ = clock64();
+#define PHASE_DECL long long ph_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long ph_t_ = clock64(); long long fq_ = 0;
+#define FINE_START { fq_ = clock64(); }
+#define FINE_MARK(i) { long long n_ = clock64(); ph_[i] += n_ - fq_; fq_ = n_; }
 #define PHASE_MARK(i) { long long n_ = clock64(); ph_[i] += n_ - ph_t_; ph_t_ = n_; }
 #define PHASE_PRINT if (blockIdx.x == 0 && threadIdx.x == 0) printf("phase cycles/step: split %.0f  propose %.0f  eval %.0f  accept %.0f  store %.0f\n", \
-    (double)ph_[0] / P.nsteps, (double)ph_[1] / P.nsteps, (double)ph_[2] / P.nsteps, (double)ph_[3] / P.nsteps, (double)ph_[4] / P.nsteps);
+    (double)ph_[0] / P.nsteps, (double)ph_[1] / P.nsteps, (double)ph_[2] / P.nsteps, (double)ph_[3] / P.nsteps, (double)ph_[4] / P.nsteps); \
+  if (blockIdx.x == 0 && threadIdx.x == 0) printf("fine (thread 0) cycles/step: %.0f %.0f %.0f %.0f %.0f %.0f\n", (double)ph_[6] / P.nsteps, (double)ph_[7] / P.nsteps, (double)ph_[8] / P.nsteps, (double)ph_[9] / P.nsteps, (double)ph_[10] / P.nsteps, (double)ph_[11] / P.nsteps);
 #else
+#define FINE_START
+#define FINE_MARK(i)
 #define PHASE_DECL
 #define PHASE_MARK(i)
 #define PHASE_PRINT
@@ -56,23 +61,26 @@ struct SamplerSmem {
   double* lp;      // [W]
   double* prop;    // [rows_pad][ndim]
   double* chi;     // [rows_pad]
-  double* fac;     // [rows_pad]  stretch factor zz of the proposal
+  double* zz;      // [2][rows_pad]  stretch factors, double-buffered by half-step parity
+  double* u2;      // [rows_pad]     acceptance uniforms (FP64 fallback of the accept test)
   double* bnd;     // [2][ndim]
   double* red;     // [kWarps]
-  long long* bkey; // [2][ndim] ordered-integer image of bnd (NaN bounds never match)
-  uint32_t* keys;  // [W]
-  int* list;       // [W]   walker at rank
+  long long* bkey; // [2][ndim] ordered-integer image of bnd
+  float* lf;       // [rows_pad]     (ndim-1) ln zz - ln u in FP32 (accept filter)
+  uint32_t* keys;  // [Wpad4]        shuffle keys of the NEXT step
+  int* list;       // [2][W]         walker at rank, double-buffered by step parity
   int* acc;        // [W]
   int* inb;        // [rows_pad]
+  int* partner;    // [rows_pad]     index into the complementary half
 };
 
 __host__ __device__ inline int sampler_rows_pad(int W) { return ceil_div((W + 1) / 2, 16) * 16; }
 
 __host__ __device__ inline size_t sampler_smem_bytes(int W, int ndim) {
   const int rp = sampler_rows_pad(W);
-  size_t dbl = (size_t)W * ndim + W + (size_t)rp * ndim + rp + rp + 4 * ndim + kWarps;
-  size_t ints = (size_t)W * 3 + 4 + rp;
-  return dbl * 8 + ints * 4 + 32;
+  size_t dbl = (size_t)W * ndim + W + (size_t)rp * ndim + rp + 2 * rp + rp + 4 * ndim + kWarps;
+  size_t words = (size_t)rp + (W + 4) + 2 * W + W + rp + rp;
+  return dbl * 8 + words * 4 + 32;
 }
 
 __device__ inline void sampler_carve(SamplerSmem& s, double* base, int W, int ndim) {
@@ -81,14 +89,17 @@ __device__ inline void sampler_carve(SamplerSmem& s, double* base, int W, int nd
   s.lp = base; base += W;
   s.prop = base; base += (size_t)rp * ndim;
   s.chi = base; base += rp;
-  s.fac = base; base += rp;
+  s.zz = base; base += 2 * rp;
+  s.u2 = base; base += rp;
   s.bnd = base; base += 2 * ndim;
   s.red = base; base += kWarps;
   s.bkey = reinterpret_cast<long long*>(base); base += 2 * ndim;
   s.keys = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(base) + 15) & ~uintptr_t(15));   // LDS.128
-  s.list = reinterpret_cast<int*>(s.keys + ((W + 3) & ~3));
-  s.acc = s.list + W;
+  s.lf = reinterpret_cast<float*>(s.keys + ((W + 3) & ~3));
+  s.list = reinterpret_cast<int*>(s.lf + rp);
+  s.acc = s.list + 2 * W;
   s.inb = s.acc + W;
+  s.partner = s.inb + rp;
 }
 
 // strict box prior, models.py:64-69 (NaN -> outside)
@@ -110,10 +121,100 @@ __device__ __forceinline__ bool in_bounds_keys(const double* th, const long long
   bool ok = true;
   for (int d = 0; d < ndim; ++d) {
     const long long k = ordered_key(th[d]);
-    ok = ok && (bkey[d] < k) && (k < bkey[ndim + d]);
+    ok = ok & (bkey[d] < k) & (k < bkey[ndim + d]);
   }
   return ok;
 }
+
+// ndim is a run-time value (1+3K, 5, 6, 2+poly_deg): a plain loop over it serialises its shared-memory
+// loads (one ~30-cycle round trip per dimension).  These helpers unroll the first kDimUnroll
+// dimensions under a predicate so all loads of a proposal are in flight together.
+constexpr int kDimUnroll = 8;
+
+// q = c - (c - s) * zz (explicitly unfused, like the oracle) -> dst ; returns the strict-prior flag
+__device__ __forceinline__ bool propose_and_check(const double* __restrict__ cj, const double* __restrict__ sk,
+                                                  double zz, double* __restrict__ dst, const long long* __restrict__ bkey,
+                                                  int ndim) {
+  bool ok = true;
+#pragma unroll
+  for (int d = 0; d < kDimUnroll; ++d) {
+    const int dd = d < ndim ? d : 0;                 // always a valid address: loads need no predicate
+    const double c = cj[dd], x = sk[dd];
+    const long long lo = bkey[dd], hi = bkey[ndim + dd];
+    const double v = __dsub_rn(c, __dmul_rn(__dsub_rn(c, x), zz));
+    const long long k = ordered_key(v);
+    if (d < ndim) {
+      dst[d] = v;
+      ok = ok & (lo < k) & (k < hi);
+    }
+  }
+  for (int d = kDimUnroll; d < ndim; ++d) {
+    const double v = __dsub_rn(cj[d], __dmul_rn(__dsub_rn(cj[d], sk[d]), zz));
+    dst[d] = v;
+    const long long k = ordered_key(v);
+    ok = ok & (bkey[d] < k) & (k < bkey[ndim + d]);
+  }
+  return ok;
+}
+
+__device__ __forceinline__ void copy_dims(double* __restrict__ dst, const double* __restrict__ src, int ndim) {
+#pragma unroll
+  for (int d = 0; d < kDimUnroll; ++d) {
+    const double v = src[d < ndim ? d : 0];
+    if (d < ndim) dst[d] = v;
+  }
+  for (int d = kDimUnroll; d < ndim; ++d) dst[d] = src[d];
+}
+
+// Side work executed INSIDE the evaluation phase: ranking the shuffle keys of the next step.  It is
+// pure integer/LDS work, so it fills issue slots that the tile loop leaves idle while its warps wait
+// for the FP64 tensor pipe; the evaluators call advance() once per column-tile iteration.
+struct RankSide {
+  const uint4* kv;   // keys, 4 per load
+  int* list_out;
+  int nchunks;       // Wpad4/4
+  int W;
+  int pos, rank, step;
+  uint32_t ki;
+  bool on;
+  __device__ __forceinline__ void begin(const uint32_t* keys, int* list, int W_, int iters) {
+    kv = reinterpret_cast<const uint4*>(keys);
+    list_out = list;
+    W = W_;
+    nchunks = ((W_ + 3) & ~3) >> 2;
+    on = list != nullptr;
+    pos = 0;
+    rank = 0;
+    step = iters > 0 ? (nchunks + iters - 1) / iters : nchunks;
+    ki = (on && (int)threadIdx.x < W_) ? keys[threadIdx.x] : 0u;
+  }
+  __device__ __forceinline__ void advance() {
+    if (!on) return;
+    const int end = min(nchunks, pos + step);
+    for (; pos < end; ++pos) {
+      const uint4 k4 = kv[pos];
+      rank += (k4.x < ki) + (k4.y < ki) + (k4.z < ki) + (k4.w < ki);
+    }
+  }
+  __device__ __forceinline__ void finish() {
+    if (!on) return;
+    for (; pos < nchunks; ++pos) {
+      const uint4 k4 = kv[pos];
+      rank += (k4.x < ki) + (k4.y < ki) + (k4.z < ki) + (k4.w < ki);
+    }
+    if ((int)threadIdx.x < W) list_out[rank] = threadIdx.x;
+    for (int i = threadIdx.x + kThreads; i < W; i += kThreads) {   // W > 256: remaining walkers, not interleaved
+      const uint32_t k = reinterpret_cast<const uint32_t*>(kv)[i];
+      int r = 0;
+      for (int c = 0; c < nchunks; ++c) {
+        const uint4 k4 = kv[c];
+        r += (k4.x < k) + (k4.y < k) + (k4.z < k) + (k4.w < k);
+      }
+      list_out[r] = i;
+    }
+    on = false;
+  }
+};
 
 // Evaluator adaptors -------------------------------------------------------------------
 template <int KC>
@@ -132,8 +233,9 @@ struct DecompEvaluator {
     decomp_init(sm, sh, d.c_exp, w, taus, log_taus, y, yerr, red);
   }
   __device__ double llconst() const { return sm.llconst; }
-  __device__ void eval_chi(const double* prop, int ndim, int nrows, double* chi) {
-    decomp_eval_chi<KC>(sm, sh, prop, ndim, nrows, rows_pad, chi);
+  __device__ int iters_per_warp(int nrows) const { return decomp_iters_per_warp(sh, nrows); }
+  __device__ void eval_chi(const double* prop, int ndim, int nrows, double* chi, RankSide& side) {
+    decomp_eval_chi<KC>(sm, sh, prop, ndim, nrows, rows_pad, chi, side);
   }
 };
 
@@ -153,7 +255,9 @@ struct DecompRCEvaluator {
     decomp_rc_init(sm, sh, d.c_exp, w, taus, log_taus, y, yerr, red);
   }
   __device__ double llconst() const { return sm.llconst; }
-  __device__ void eval_chi(const double* prop, int ndim, int nrows, double* chi) {
+  __device__ int iters_per_warp(int) const { return 0; }
+  __device__ void eval_chi(const double* prop, int ndim, int nrows, double* chi, RankSide& side) {
+    side.finish();
     decomp_rc_eval_chi(sm, sh, prop, ndim, nrows, rows_pad, chi);
   }
 };
@@ -175,7 +279,9 @@ struct DecompTF32Evaluator {
     decomp_tf32_init<PREC>(sm, sh, d.c_exp, w, taus, log_taus, y, yerr, red);
   }
   __device__ double llconst() const { return sm.llconst; }
-  __device__ void eval_chi(const double* prop, int ndim, int nrows, double* chi) {
+  __device__ int iters_per_warp(int) const { return 0; }
+  __device__ void eval_chi(const double* prop, int ndim, int nrows, double* chi, RankSide& side) {
+    side.finish();
     decomp_tf32_eval_chi<PREC>(sm, sh, prop, ndim, nrows, rows_pad, chi);
   }
 };
@@ -193,7 +299,9 @@ struct VecEvaluator {
     vec_init(sm, N, w, y, yerr, red);
   }
   __device__ double llconst() const { return sm.llconst; }
-  __device__ void eval_chi(const double* prop, int ndim, int nrows, double* chi) {
+  __device__ int iters_per_warp(int) const { return 0; }
+  __device__ void eval_chi(const double* prop, int ndim, int nrows, double* chi, RankSide& side) {
+    side.finish();
     vec_eval_chi<Row>(sm, N, n_modes, prop, ndim, nrows, chi);
   }
 };
@@ -266,11 +374,13 @@ __global__ void __launch_bounds__(kThreads, MINB) ensemble_kernel(const Ensemble
   int flag = 0;
 
   // log-probability of p0, in two passes of <= H0 rows
+  RankSide side;
+  side.begin(s.keys, nullptr, W, 0);
   for (int pass = 0; pass < 2; ++pass) {
     const int off = pass ? H0 : 0, n = pass ? W - H0 : H0;
     for (int i = tid; i < n * ndim; i += kThreads) s.prop[i] = s.coords[off * ndim + i];
     __syncthreads();
-    ev.eval_chi(s.prop, ndim, n, s.chi);
+    ev.eval_chi(s.prop, ndim, n, s.chi, side);
     __syncthreads();
     for (int q = tid; q < n; q += kThreads) {
       const double v = in_bounds(s.prop + q * ndim, s.bnd, ndim) ? -0.5 * (s.chi[q] + llc) : neg_inf();
@@ -283,95 +393,123 @@ __global__ void __launch_bounds__(kThreads, MINB) ensemble_kernel(const Ensemble
   const uint32_t k0 = (uint32_t)P.seed, k1 = (uint32_t)(P.seed >> 32);
   const uint32_t spec = P.spectrum0 + (uint32_t)b;
   const int first = P.discard + P.thin - 1;
-    int kept = 0;
+  const int Wpad4 = (W + 3) & ~3;
+  int kept = 0;
+
+  // ---- work that depends only on the Philox stream runs one phase AHEAD of its use, on threads that
+  //      would otherwise idle, so that the serial phases between two evaluations stay short ----------
+  // shuffle keys of step t (emcee: shuffle(arange(W) % 2)): one Philox call feeds 4 walkers
+  auto gen_keys = [&](uint32_t t, int worker, int nworkers) {
+    for (int c = worker; c < Wpad4 / 4; c += nworkers) {
+      const u32x4 r = philox4x32_10((uint32_t)c, t, spec, 0u, k0, k1);
+      const uint32_t wd[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = 4 * c + e;
+        s.keys[i] = i < W ? ((wd[e] & ~P.kmask) | (uint32_t)i) : 0xffffffffu;   // padding sorts last
+      }
+    }
+  };
+  // proposal draws of half-step (t, sp): stretch factor zz and partner index
+  auto gen_proposal_draws = [&](uint32_t t, int sp, int worker, int nworkers) {
+    const int Hs = sp ? W - H0 : H0, Nc = W - Hs;
+    double* zzb = s.zz + (size_t)sp * rows_pad;
+    for (int q = worker; q < Hs; q += nworkers) {
+      const u32x4 r = philox4x32_10((uint32_t)q, t, spec, (uint32_t)(1 + 2 * sp), k0, k1);
+      const double u = u53(r.x, r.y);
+      const double zr = __dadd_rn(__dmul_rn(P.a - 1.0, u), 1.0);
+      zzb[q] = P.a_pow2 ? __dmul_rn(__dmul_rn(zr, zr), P.inv_a) : __ddiv_rn(__dmul_rn(zr, zr), P.a);
+      s.partner[q] = (int)__umulhi(r.z, (uint32_t)Nc);
+    }
+  };
+
+  // prologue: split of step 0 and the draws of its first half-step
+  gen_keys((uint32_t)P.step0, tid, kThreads);
+  __syncthreads();
+  side.begin(s.keys, s.list, W, 0);
+  side.finish();
+  gen_proposal_draws((uint32_t)P.step0, 0, tid, kThreads);
+  __syncthreads();
 
   PHASE_DECL
   for (int it = 0; it < P.nsteps; ++it) {
     const uint32_t t = (uint32_t)(P.step0 + it);
+    const int* list = s.list + (size_t)(it & 1) * W;          // this step's split
+    int* list_next = s.list + (size_t)((it + 1) & 1) * W;
     PHASE_MARK(5)
-    // ---- random equal split (emcee: shuffle(arange(W) % 2)) ------------------------------
-    const int Wpad4 = (W + 3) & ~3;
-    for (int i = tid; i < Wpad4; i += kThreads) {
-      uint32_t key = 0xffffffffu;                       // padding sorts last, never counted
-      if (i < W) {
-        const u32x4 r = philox4x32_10((uint32_t)(i >> 2), t, spec, 0u, k0, k1);
-        const int sel = i & 3;
-        const uint32_t word = sel == 0 ? r.x : sel == 1 ? r.y : sel == 2 ? r.z : r.w;
-        key = (word & ~P.kmask) | (uint32_t)i;
-      }
-      s.keys[i] = key;
-    }
-    __syncthreads();
-    for (int i = tid; i < W; i += kThreads) {
-      const uint32_t ki = s.keys[i];
-      const uint4* kv = reinterpret_cast<const uint4*>(s.keys);
-      int rank = 0;
-#pragma unroll 4
-      for (int j = 0; j < Wpad4 / 4; ++j) {
-        const uint4 k4 = kv[j];
-        rank += (k4.x < ki) + (k4.y < ki) + (k4.z < ki) + (k4.w < ki);
-      }
-      s.list[rank] = i;
-    }
-    __syncthreads();
-    PHASE_MARK(0)
-
     for (int sp = 0; sp < 2; ++sp) {
       const int off = sp ? H0 : 0, Hs = sp ? W - H0 : H0;
-      const int coff = sp ? 0 : H0, Nc = W - Hs;
-      // ---- stretch proposals q = c_j - (c_j - s_k) zz -------------------------------------
-      for (int q = tid; q < Hs; q += kThreads) {
-        const u32x4 r = philox4x32_10((uint32_t)q, t, spec, (uint32_t)(1 + 2 * sp), k0, k1);
-        const double u = u53(r.x, r.y);
-        const double zr = __dadd_rn(__dmul_rn(P.a - 1.0, u), 1.0);
-        const double zz = P.a_pow2 ? __dmul_rn(__dmul_rn(zr, zr), P.inv_a) : __ddiv_rn(__dmul_rn(zr, zr), P.a);
-        const int j = s.list[coff + (int)__umulhi(r.z, (uint32_t)Nc)];
-        const int k = s.list[off + q];
-        const double* cj = s.coords + j * ndim;
-        const double* sk = s.coords + k * ndim;
-        double* dst = s.prop + q * ndim;
-        for (int d = 0; d < ndim; ++d) dst[d] = __dsub_rn(cj[d], __dmul_rn(__dsub_rn(cj[d], sk[d]), zz));
-        s.fac[q] = zz;
-        s.inb[q] = in_bounds_keys(dst, s.bkey, ndim) ? 1 : 0;
+      const int coff = sp ? 0 : H0;
+      const double* zzb = s.zz + (size_t)sp * rows_pad;
+      // ---- PROPOSE: threads [0,Hs) build q = c_j - (c_j - s_k) zz ; the other threads draw the
+      //      acceptance uniforms of this half-step and the FP32 image of the accept threshold ----------
+      for (int idx = tid; idx < 2 * Hs; idx += kThreads) {
+        if (idx < Hs) {
+          const int q = idx;
+          const int j = list[coff + s.partner[q]];
+          const int k = list[off + q];
+          s.inb[q] = propose_and_check(s.coords + j * ndim, s.coords + k * ndim, zzb[q], s.prop + q * ndim, s.bkey, ndim) ? 1 : 0;
+        } else {
+          const int q = idx - Hs;
+          const u32x4 r = philox4x32_10((uint32_t)q, t, spec, (uint32_t)(2 + 2 * sp), k0, k1);
+          const double u2 = u53(r.x, r.y);
+          s.u2[q] = u2;
+          s.lf[q] = (float)(ndim - 1) * logf((float)zzb[q]) - logf((float)u2);
+        }
       }
       __syncthreads();
       PHASE_MARK(1)
-      // ---- fused forward + chi^2 for all proposals ------------------------------------------
-      ev.eval_chi(s.prop, ndim, Hs, s.chi);
+      // ---- EVAL: fused forward + chi^2 of all proposals ----------------------------------------------
+      ev.eval_chi(s.prop, ndim, Hs, s.chi, side);
       __syncthreads();
       PHASE_MARK(2)
-      // ---- accept / reject ---------------------------------------------------------------------
-      for (int q = tid; q < Hs; q += kThreads) {
-        const u32x4 r = philox4x32_10((uint32_t)q, t, spec, (uint32_t)(2 + 2 * sp), k0, k1);
-        const double u2 = u53(r.x, r.y);
-        const int k = s.list[off + q];
-        const double lpn = s.inb[q] ? -0.5 * (s.chi[q] + llc) : neg_inf();
-        if (lpn != lpn) flag |= 1;
-        // emcee: accept iff (ndim-1) ln zz + lp' - lp > ln u.  The two logarithms are first
-        // taken in FP32 (SFU/FMA pipes, |error| < 1e-5): unless the margin is below 1e-4 the FP64
-        // decision is already determined; otherwise (about 1 proposal in 10^4) it is recomputed in
-        // FP64 exactly as the oracle does.  Both paths give the decision of the FP64 formula.
-        const double dlp = __dsub_rn(lpn, s.lp[k]);
-        const double zz = s.fac[q];
-        const float lf = (float)(ndim - 1) * logf((float)zz) - logf((float)u2);
-        const double est = dlp + (double)lf;
-        bool accept;
-        if (fabs(est) > fma(1e-15, fabs(lpn) + fabs(s.lp[k]), 1e-4)) {   // margin >> FP32 + FP64 rounding
-          accept = est > 0.0;
-        } else {
-          const double lnpdiff = __dsub_rn(__dadd_rn(__dmul_rn((double)(ndim - 1), log(zz)), lpn), s.lp[k]);
-          accept = lnpdiff > log(u2);
+      // ---- ACCEPT (threads [0,Hs)) ; the other threads draw the proposal factors of the next
+      //      half-step, and after the first half-step the first threads also draw the next step's keys --------
+      for (int idx = tid; idx < 2 * Hs; idx += kThreads) {
+        if (idx < Hs) {
+          const int q = idx;
+          const int k = list[off + q];
+          const double lpo = s.lp[k];
+          const double lpn = s.inb[q] ? -0.5 * (s.chi[q] + llc) : neg_inf();
+          if (lpn != lpn) flag |= 1;
+          // emcee: accept iff (ndim-1) ln zz + lp' - lp > ln u.  The logarithms were taken in FP32
+          // (|error| < 1e-5): unless the margin is below the threshold the FP64 decision is already
+          // determined; otherwise (about 1 proposal in 10^4) it is recomputed in FP64 as the oracle does.
+          const double est = __dsub_rn(lpn, lpo) + (double)s.lf[q];
+          bool accept;
+          if (fabs(est) > fma(1e-15, fabs(lpn) + fabs(lpo), 1e-4)) {
+            accept = est > 0.0;
+          } else {
+            const double lnpdiff = __dsub_rn(__dadd_rn(__dmul_rn((double)(ndim - 1), log(zzb[q])), lpn), lpo);
+            accept = lnpdiff > log(s.u2[q]);
+          }
+          if (accept) {
+            copy_dims(s.coords + k * ndim, s.prop + q * ndim, ndim);
+            s.lp[k] = lpn;
+            s.acc[k] += 1;
+          }
         }
-        if (accept) {
-          for (int d = 0; d < ndim; ++d) s.coords[k * ndim + d] = s.prop[q * ndim + d];
-          s.lp[k] = lpn;
-          s.acc[k] += 1;
-        }
+      }
+      {
+        // spare threads (those beyond the Hs acceptors) prepare the next half-step
+        const int nspare = kThreads - min(Hs, kThreads);
+        const bool spare = tid >= Hs;
+        const int worker = spare ? tid - Hs : tid, nworkers = spare ? nspare : kThreads;
+        if (spare || nspare == 0)
+          gen_proposal_draws(sp == 0 ? t : t + 1u, sp ^ 1, worker, nworkers);
+        if (sp == 0 && (!spare || Hs >= kThreads)) gen_keys(t + 1u, tid, min(Hs, kThreads));
       }
       __syncthreads();
       PHASE_MARK(3)
     }
+    // ---- split of the next step: rank its keys (drawn during this step's first accept phase) ---------
+    side.begin(s.keys, list_next, W, 0);
+    side.finish();
+    PHASE_MARK(0)
     // ---- backend.save_step: chain[it] = coords ; log_prob[it] = lp -----------------------------
+    // (no barrier needed in between: the next reader of list_next / coords is behind the barrier
+    //  that ends the next PROPOSE phase... the proposals read list_next, so synchronise here)
+    __syncthreads();
     if (it >= first && (it - first) % P.thin == 0) {
       if (P.chain != nullptr && writer) {
         double* dst = P.chain + ((size_t)b * P.nkeep + kept) * W * ndim;
