@@ -71,6 +71,16 @@ int device_smem_optin() {
 // grid (chunks, B): CTA (c, b) handles theta rows [c*kRows, ...) of spectrum b, striding by gridDim.x.
 constexpr int kRows = 128;
 
+// Resident CTAs per SM the vector-model ensemble kernels are compiled for (register cap
+// 65536/(256*n)).  Their evaluation phase is short, so the serial phases of the stretch move
+// (split, proposals, accept) are ~half of a step: more co-resident spectra hide them.  Values from
+// the sweep in profiles/r01c_vec_occupancy.md (W=128, N=64).
+#ifdef BISIP_VEC_MINB
+constexpr int kMinBDias = BISIP_VEC_MINB, kMinBShin = BISIP_VEC_MINB, kMinBCC = BISIP_VEC_MINB;
+#else
+constexpr int kMinBDias = 4, kMinBShin = 3, kMinBCC = 4;
+#endif
+
 struct BatchParams {
   bisip_model_desc d;
   int B, n_theta;
@@ -421,18 +431,18 @@ int bisip_ensemble_run(const bisip_model_desc* desc, int n_spectra, int n_walker
     case BISIP_MODEL_COLECOLE:
       smem += VecEvaluator<ColeColeRow>::smem_doubles(*desc, rp) * 8;
       switch (desc->n_modes) {
-        case 1: return launch(ensemble_kernel<VecEvaluator<ColeColeRowT<1>>, 2>, grid, smem, st, "ensemble_colecole", &P);
-        case 2: return launch(ensemble_kernel<VecEvaluator<ColeColeRowT<2>>, 2>, grid, smem, st, "ensemble_colecole", &P);
+        case 1: return launch(ensemble_kernel<VecEvaluator<ColeColeRowT<1>>, kMinBCC>, grid, smem, st, "ensemble_colecole", &P);
+        case 2: return launch(ensemble_kernel<VecEvaluator<ColeColeRowT<2>>, kMinBCC>, grid, smem, st, "ensemble_colecole", &P);
         case 3: return launch(ensemble_kernel<VecEvaluator<ColeColeRowT<3>>, 2>, grid, smem, st, "ensemble_colecole", &P);
         case 4: return launch(ensemble_kernel<VecEvaluator<ColeColeRowT<4>>, 1>, grid, smem, st, "ensemble_colecole", &P);
         default: return launch(ensemble_kernel<VecEvaluator<ColeColeRow>, 1>, grid, smem, st, "ensemble_colecole", &P);
       }
     case BISIP_MODEL_DIAS:
       smem += VecEvaluator<DiasRow>::smem_doubles(*desc, rp) * 8;
-      return launch(ensemble_kernel<VecEvaluator<DiasRow>, 2>, grid, smem, st, "ensemble_dias", &P);
+      return launch(ensemble_kernel<VecEvaluator<DiasRow>, kMinBDias>, grid, smem, st, "ensemble_dias", &P);
     case BISIP_MODEL_SHIN:
       smem += VecEvaluator<ShinRow>::smem_doubles(*desc, rp) * 8;
-      return launch(ensemble_kernel<VecEvaluator<ShinRow>, 2>, grid, smem, st, "ensemble_shin", &P);
+      return launch(ensemble_kernel<VecEvaluator<ShinRow>, kMinBShin>, grid, smem, st, "ensemble_shin", &P);
     default: {
       if (use_rc(*desc)) {
         RcPlan plan;

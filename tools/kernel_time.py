@@ -12,14 +12,15 @@ ap.add_argument("--model", default="decomp"); ap.add_argument("--B", type=int, d
 ap.add_argument("--W", type=int, default=256); ap.add_argument("--T", type=int, default=500)
 ap.add_argument("--N", type=int, default=64); ap.add_argument("--S", type=int, default=64)
 ap.add_argument("--P", type=int, default=4); ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--K", type=int, default=1)
 ap.add_argument("--precision", default="fp64"); ap.add_argument("--c_exp", type=float, default=1.0)
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 _, w = synthetic.frequencies(a.N)
-kw = dict(poly_deg=a.P, n_tau=a.S, c_exp=a.c_exp, precision=a.precision) if a.model == "decomp" else {}
+kw = dict(poly_deg=a.P, n_tau=a.S, c_exp=a.c_exp, precision=a.precision) if a.model == "decomp" else (dict(n_modes=a.K) if a.model == "colecole" else {})
 probe = BatchInversion(a.model, w, np.zeros((1, 2, a.N)), np.ones((1, 2, a.N)), device=dev, **kw)
 fwd = lambda th, ww: engine.forward(probe._spec(), _lib.dev_f64(th[:, None, :], dev), _lib.dev_f64(ww, dev))[:, 0].cpu().numpy()
-syn = synthetic.make(a.model, 0, a.B, fwd, N=a.N, poly_deg=a.P)
+syn = synthetic.make(a.model, 0, a.B, fwd, N=a.N, poly_deg=a.P, n_modes=a.K)
 inv = BatchInversion(a.model, w, syn["zn"], syn["zn_err"], nwalkers=a.W, nsteps=a.T, seed=1, device=dev, **kw)
 p0 = _lib.dev_f64(inv.draw_p0(0, a.B), dev)
 y, ye = _lib.dev_f64(syn["zn"], dev), _lib.dev_f64(syn["zn_err"], dev)
