@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kThreads) vec_batch_kernel(const BatchParams P
   extern __shared__ __align__(16) double smem[];
   const int b = blockIdx.y, ndim = P.d.ndim, N = P.d.n_freq;
   VecSmem s;
-  double* p = vec_carve(s, smem, N);
+  double* p = vec_carve(s, smem, N, kRows, Row::kRC);
   double* prop = p; p += kRows * ndim;
   double* chi = p; p += kRows;
   double* bnd = p; p += 2 * ndim;
@@ -143,10 +143,12 @@ __global__ void __launch_bounds__(kThreads) vec_batch_kernel(const BatchParams P
     const double* th = P.theta + ((size_t)b * P.n_theta + r0) * ndim;
     for (int i = threadIdx.x; i < kRows * ndim; i += kThreads) prop[i] = (i < n * ndim) ? th[i] : 0.0;
     __syncthreads();
+    vec_prepare_rows<Row>(s, P.d.n_modes, prop, ndim, n);
+    __syncthreads();
     if (WANT_Z) {
-      vec_eval_Z<Row>(s, N, P.d.n_modes, prop, ndim, n, P.Z + ((size_t)b * P.n_theta + r0) * 2 * N);
+      vec_eval_Z<Row>(s, N, P.d.n_modes, n, P.Z + ((size_t)b * P.n_theta + r0) * 2 * N);
     } else {
-      vec_eval_chi<Row>(s, N, P.d.n_modes, prop, ndim, n, chi);
+      vec_eval_chi<Row>(s, N, P.d.n_modes, n, chi);
       __syncthreads();
       for (int q = threadIdx.x; q < n; q += kThreads)
         P.lp[(size_t)b * P.n_theta + r0 + q] =
@@ -156,12 +158,28 @@ __global__ void __launch_bounds__(kThreads) vec_batch_kernel(const BatchParams P
   }
 }
 
+// per-proposal constants of the vector-model kernel that check_desc()/run_batch() will pick
+int vec_row_consts(const bisip_model_desc& d) {
+  switch (d.model) {
+    case BISIP_MODEL_DIAS: return DiasRow::kRC;
+    case BISIP_MODEL_SHIN: return ShinRow::kRC;
+    default:
+      switch (d.n_modes) {
+        case 1: return ColeColeRowT<1>::kRC;
+        case 2: return ColeColeRowT<2>::kRC;
+        case 3: return ColeColeRowT<3>::kRC;
+        case 4: return ColeColeRowT<4>::kRC;
+        default: return ColeColeRow::kRC;
+      }
+  }
+}
+
 size_t batch_smem_bytes(const bisip_model_desc& d) {
   size_t dbl = (size_t)kRows * d.ndim + kRows + 2 * d.ndim + kWarps;
   if (d.model == BISIP_MODEL_DECOMP)
     dbl += decomp_smem_doubles(DecompShape(d.n_freq, d.n_tau, d.n_coef), kRows);
   else
-    dbl += vec_smem_doubles(d.n_freq);
+    dbl += vec_smem_doubles(d.n_freq, kRows, vec_row_consts(d));
   return dbl * 8;
 }
 
@@ -429,7 +447,7 @@ int bisip_ensemble_run(const bisip_model_desc* desc, int n_spectra, int n_walker
   dim3 grid(n_spectra);
   switch (desc->model) {
     case BISIP_MODEL_COLECOLE:
-      smem += VecEvaluator<ColeColeRow>::smem_doubles(*desc, rp) * 8;
+      smem += vec_smem_doubles(desc->n_freq, rp, vec_row_consts(*desc)) * 8;
       switch (desc->n_modes) {
         case 1: return launch(ensemble_kernel<VecEvaluator<ColeColeRowT<1>>, kMinBCC>, grid, smem, st, "ensemble_colecole", &P);
         case 2: return launch(ensemble_kernel<VecEvaluator<ColeColeRowT<2>>, kMinBCC>, grid, smem, st, "ensemble_colecole", &P);

@@ -169,48 +169,66 @@ __device__ __forceinline__ void copy_dims(double* __restrict__ dst, const double
 // Side work executed INSIDE the evaluation phase: ranking the shuffle keys of the next step.  It is
 // pure integer/LDS work, so it fills issue slots that the tile loop leaves idle while its warps wait
 // for the FP64 tensor pipe; the evaluators call advance() once per column-tile iteration.
+// count of the 4 keys of shared-memory chunk `saddr` (32-bit shared address) that are below ki:
+// one LDS.128 + (ISETP, predicated add) per key, four independent counters
+__device__ __forceinline__ void rank_chunk(uint32_t saddr, uint32_t ki, int& r0, int& r1, int& r2, int& r3) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p0, p1, p2, p3;\n\t"
+      ".reg .u32 k0, k1, k2, k3;\n\t"
+      "ld.shared.v4.u32 {k0, k1, k2, k3}, [%4];\n\t"
+      "setp.lt.u32 p0, k0, %5;\n\t"
+      "setp.lt.u32 p1, k1, %5;\n\t"
+      "setp.lt.u32 p2, k2, %5;\n\t"
+      "setp.lt.u32 p3, k3, %5;\n\t"
+      "@p0 add.s32 %0, %0, 1;\n\t"
+      "@p1 add.s32 %1, %1, 1;\n\t"
+      "@p2 add.s32 %2, %2, 1;\n\t"
+      "@p3 add.s32 %3, %3, 1;\n\t"
+      "}"
+      : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3)
+      : "r"(saddr), "r"(ki));
+}
+
 struct RankSide {
-  const uint4* kv;   // keys, 4 per load
+  uint32_t kaddr;    // shared-memory address of the keys (4 per 16-byte chunk)
+  const uint32_t* keys;
   int* list_out;
   int nchunks;       // Wpad4/4
   int W;
-  int pos, rank, step;
+  int pos, step;
+  int r0, r1, r2, r3;
   uint32_t ki;
   bool on;
-  __device__ __forceinline__ void begin(const uint32_t* keys, int* list, int W_, int iters) {
-    kv = reinterpret_cast<const uint4*>(keys);
+  __device__ __forceinline__ void begin(const uint32_t* keys_, int* list, int W_, int iters) {
+    keys = keys_;
+    kaddr = (uint32_t)__cvta_generic_to_shared(keys_);
     list_out = list;
     W = W_;
     nchunks = ((W_ + 3) & ~3) >> 2;
     on = list != nullptr;
     pos = 0;
-    rank = 0;
+    r0 = r1 = r2 = r3 = 0;
     step = iters > 0 ? (nchunks + iters - 1) / iters : nchunks;
-    ki = (on && (int)threadIdx.x < W_) ? keys[threadIdx.x] : 0u;
+    ki = (on && (int)threadIdx.x < W_) ? keys_[threadIdx.x] : 0u;
   }
   __device__ __forceinline__ void advance() {
     if (!on) return;
     const int end = min(nchunks, pos + step);
-    for (; pos < end; ++pos) {
-      const uint4 k4 = kv[pos];
-      rank += (k4.x < ki) + (k4.y < ki) + (k4.z < ki) + (k4.w < ki);
-    }
+    for (; pos < end; ++pos) rank_chunk(kaddr + 16u * pos, ki, r0, r1, r2, r3);
   }
   __device__ __forceinline__ void finish() {
     if (!on) return;
-    for (; pos < nchunks; ++pos) {
-      const uint4 k4 = kv[pos];
-      rank += (k4.x < ki) + (k4.y < ki) + (k4.z < ki) + (k4.w < ki);
+    if ((int)threadIdx.x < W) {                       // warps without walkers skip the count
+#pragma unroll 4
+      for (; pos < nchunks; ++pos) rank_chunk(kaddr + 16u * pos, ki, r0, r1, r2, r3);
+      list_out[(r0 + r1) + (r2 + r3)] = threadIdx.x;
     }
-    if ((int)threadIdx.x < W) list_out[rank] = threadIdx.x;
     for (int i = threadIdx.x + kThreads; i < W; i += kThreads) {   // W > 256: remaining walkers, not interleaved
-      const uint32_t k = reinterpret_cast<const uint32_t*>(kv)[i];
-      int r = 0;
-      for (int c = 0; c < nchunks; ++c) {
-        const uint4 k4 = kv[c];
-        r += (k4.x < k) + (k4.y < k) + (k4.z < k) + (k4.w < k);
-      }
-      list_out[r] = i;
+      const uint32_t k = keys[i];
+      int a = 0, b = 0, c = 0, d = 0;
+      for (int ch = 0; ch < nchunks; ++ch) rank_chunk(kaddr + 16u * ch, k, a, b, c, d);
+      list_out[(a + b) + (c + d)] = i;
     }
     on = false;
   }
@@ -220,6 +238,8 @@ struct RankSide {
 template <int KC>
 struct DecompEvaluator {
   static constexpr bool kClustered = false;
+  static constexpr bool kNeedsPrepare = false;
+  __device__ __forceinline__ void prepare_row(int, const double*) {}
   DecompSmem sm;
   DecompShape sh;
   int rows_pad;
@@ -242,6 +262,8 @@ struct DecompEvaluator {
 // Large tau grids: stage 1 recomputed per k chunk, frequency columns split over a CTA cluster.
 struct DecompRCEvaluator {
   static constexpr bool kClustered = true;
+  static constexpr bool kNeedsPrepare = false;
+  __device__ __forceinline__ void prepare_row(int, const double*) {}
   DecompRCSmem sm;
   DecompRCShape sh;
   int rows_pad;
@@ -266,6 +288,8 @@ struct DecompRCEvaluator {
 template <int PREC>
 struct DecompTF32Evaluator {
   static constexpr bool kClustered = true;
+  static constexpr bool kNeedsPrepare = false;
+  __device__ __forceinline__ void prepare_row(int, const double*) {}
   DecompTF32Smem sm;
   DecompRCShape sh;
   int rows_pad;
@@ -289,20 +313,27 @@ struct DecompTF32Evaluator {
 template <class Row>
 struct VecEvaluator {
   static constexpr bool kClustered = false;
+  static constexpr bool kNeedsPrepare = true;
   VecSmem sm;
   int N, n_modes;
   __device__ VecEvaluator(const bisip_model_desc& d, int, int) : N(d.n_freq), n_modes(d.n_modes) {}
-  static __host__ size_t smem_doubles(const bisip_model_desc& d, int) { return vec_smem_doubles(d.n_freq); }
-  __device__ double* carve(double* base, int) { return vec_carve(sm, base, N); }
+  static __host__ size_t smem_doubles(const bisip_model_desc& d, int rows_pad) {
+    return vec_smem_doubles(d.n_freq, rows_pad, Row::kRC);
+  }
+  __device__ double* carve(double* base, int rp) { return vec_carve(sm, base, N, rp, Row::kRC); }
   __device__ void init(const bisip_model_desc&, const double* w, const double*, const double*, const double* y,
                        const double* yerr, double* red) {
     vec_init(sm, N, w, y, yerr, red);
   }
   __device__ double llconst() const { return sm.llconst; }
   __device__ int iters_per_warp(int) const { return 0; }
-  __device__ void eval_chi(const double* prop, int ndim, int nrows, double* chi, RankSide& side) {
+  // theta-only constants of proposal q (exp / sincospi / divisions), by the thread that built it
+  __device__ __forceinline__ void prepare_row(int q, const double* th) {
+    Row::prepare(th, n_modes, sm.rowc + (size_t)q * Row::kRC);
+  }
+  __device__ void eval_chi(const double*, int, int nrows, double* chi, RankSide& side) {
     side.finish();
-    vec_eval_chi<Row>(sm, N, n_modes, prop, ndim, nrows, chi);
+    vec_eval_chi<Row>(sm, N, n_modes, nrows, chi);
   }
 };
 
@@ -380,6 +411,10 @@ __global__ void __launch_bounds__(kThreads, MINB) ensemble_kernel(const Ensemble
     const int off = pass ? H0 : 0, n = pass ? W - H0 : H0;
     for (int i = tid; i < n * ndim; i += kThreads) s.prop[i] = s.coords[off * ndim + i];
     __syncthreads();
+    if (Eval::kNeedsPrepare) {
+      for (int q = tid; q < n; q += kThreads) ev.prepare_row(q, s.prop + q * ndim);
+      __syncthreads();
+    }
     ev.eval_chi(s.prop, ndim, n, s.chi, side);
     __syncthreads();
     for (int q = tid; q < n; q += kThreads) {
@@ -449,6 +484,7 @@ __global__ void __launch_bounds__(kThreads, MINB) ensemble_kernel(const Ensemble
           const int j = list[coff + s.partner[q]];
           const int k = list[off + q];
           s.inb[q] = propose_and_check(s.coords + j * ndim, s.coords + k * ndim, zzb[q], s.prop + q * ndim, s.bkey, ndim) ? 1 : 0;
+          ev.prepare_row(q, s.prop + q * ndim);
         } else {
           const int q = idx - Hs;
           const u32x4 r = philox4x32_10((uint32_t)q, t, spec, (uint32_t)(2 + 2 * sp), k0, k1);
