@@ -78,7 +78,7 @@ constexpr int kRows = 128;
 #ifdef BISIP_VEC_MINB
 constexpr int kMinBDias = BISIP_VEC_MINB, kMinBShin = BISIP_VEC_MINB, kMinBCC = BISIP_VEC_MINB;
 #else
-constexpr int kMinBDias = 4, kMinBShin = 3, kMinBCC = 4;
+constexpr int kMinBDias = 4, kMinBShin = 4, kMinBCC = 4;
 #endif
 
 struct BatchParams {
