@@ -161,6 +161,7 @@ class BatchInversion:
         ``chain`` (B, n_keep, W, ndim) and ``log_prob`` (B, n_keep, W).
         """
         dev_res = self.fit_device(p0, discard, thin, percentiles, keep_chain, batch_size)
+        self.percentiles = tuple(float(q) for q in percentiles)
         self.results = {k: v.cpu().numpy() for k, v in dev_res.items()}
         return self.results
 
@@ -198,6 +199,30 @@ class BatchInversion:
                 acc['chain'].append(res['chain'])
                 acc['log_prob'].append(res['log_prob'])
         return {k: torch.cat(v, 0) for k, v in acc.items()}
+
+    # ------------------------------------------------------------------ results
+    def rtd(self, stat='mean'):
+        """Relaxation-time distribution of every spectrum from the fitted coefficients:
+        ``stat`` = 'mean' or an index into the stored percentiles.  Returns (m (B, n_tau), total_m (B,))."""
+        from .products import relaxation_time_distribution
+        if self.model != 'decomp':
+            raise ValueError('rtd() is defined for the polynomial decomposition only')
+        if self.results is None:
+            raise AssertionError('Model is not fitted! Fit the model to a dataset before attempting to plot results.')
+        a = self.results['mean'] if stat == 'mean' else self.results['percentiles'][:, int(stat)]
+        lt = self.log_taus
+        m = (relaxation_time_distribution(a[:, 1:], lt) if lt.ndim == 2 else
+             np.stack([relaxation_time_distribution(a[b, 1:], lt[b]) for b in range(a.shape[0])]))
+        return m, m.sum(-1)
+
+    def to_csv(self, path, ids=None):
+        """One row per spectrum: id, acceptance, flags, mean/std/percentiles of every parameter."""
+        from .products import batch_table
+        if self.results is None:
+            raise AssertionError('Model is not fitted! Fit the model to a dataset before attempting to plot results.')
+        cols, table = batch_table(self.param_names, self.results, ids, self.percentiles)
+        np.savetxt(path, table, header=','.join(cols), delimiter=',', comments='')
+        return cols
 
     # ------------------------------------------------------------------ construction from files
     @classmethod

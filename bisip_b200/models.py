@@ -223,6 +223,30 @@ class PolynomialDecomposition(Inversion):
         (ascending powers — the order the reference code uses, ``models.py:228-229``)."""
         return super().forward(theta, w)
 
+    # ---- derived products: what decomposition users read off a fit (reference
+    #      docs/tutorials/decomposition.ipynb cells 25-29: get_m / total_m) ------------------------
+    def get_rtd(self, chain=None, p=None, **kwargs):
+        """Relaxation-time distribution m(tau_l) = sum_i a_i log_tau_l^i over the tau grid.
+
+        With ``p=None`` the RTD of the posterior-mean coefficients, shape ``(n_tau,)`` (the
+        tutorial's ``get_m``); with percentiles ``p`` the per-tau percentiles of the RTD over
+        the chain, shape ``(len(p), n_tau)`` (reduced on the GPU by ``bisip_column_stats``).
+        ``chain`` / ``discard`` / ``thin`` as in ``get_param_mean``."""
+        from .products import relaxation_time_distribution
+        if p is None:
+            return relaxation_time_distribution(self.get_param_mean(chain=chain, **kwargs)[1:], self.log_taus)
+        chain = self.parse_chain(chain, **kwargs)
+        m = relaxation_time_distribution(chain[:, 1:], self.log_taus)              # (n, n_tau)
+        dev = _lib.require_cuda(getattr(self, "device", None))
+        out = engine.column_stats(_lib.dev_f64(m, dev).reshape(1, m.shape[0], m.shape[1]), p=p)["pct"][0]
+        res = out.cpu().numpy()
+        return res if np.ndim(p) else res[0]
+
+    def get_total_chargeability(self, chain=None, **kwargs):
+        """Sum of the RTD of the posterior-mean coefficients over the tau grid (the tutorial's
+        ``total_m`` column)."""
+        return float(np.sum(self.get_rtd(chain=chain, **kwargs)))
+
 
 class PeltonColeCole(Inversion):
     """Generalised (multi-mode) Pelton Cole-Cole model (reference ``models.py:232-271``).

@@ -53,6 +53,15 @@ class utils(object):
         chain = self.parse_chain(chain, **kwargs)
         return self._chain_stats(chain, std=True)["std"][0].cpu().numpy()
 
+    def save_results(self, path, p=[2.5, 50, 97.5], chain=None, **kwargs):
+        """Write the parameter percentiles to a CSV in the layout of the reference quickstart
+        (``quickstart.ipynb`` cells 31-34): header = comma-joined ``param_names``, one row per
+        percentile.  Returns the (len(p), ndim) table."""
+        from .products import save_percentiles_csv
+        results = self.get_param_percentile(p=p, chain=chain, **kwargs)
+        save_percentiles_csv(path, self.param_names, results)
+        return results
+
     def parse_chain(self, chain, **kwargs):
         """Same contract as reference ``utils.py:87-106``."""
         if chain is None:

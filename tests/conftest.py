@@ -37,3 +37,9 @@ def gold_post():
 def data_files():
     from bisip_b200 import DataFiles
     return DataFiles()
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    import pathlib
+    return pathlib.Path(GOLD)
