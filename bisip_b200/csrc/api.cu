@@ -71,15 +71,22 @@ int device_smem_optin() {
 // grid (chunks, B): CTA (c, b) handles theta rows [c*kRows, ...) of spectrum b, striding by gridDim.x.
 constexpr int kRows = 128;
 
-// Resident CTAs per SM the vector-model ensemble kernels are compiled for (register cap
-// 65536/(256*n)).  Their evaluation phase is short, so the serial phases of the stretch move
-// (split, proposals, accept) are ~half of a step: more co-resident spectra hide them.  Values from
-// the sweep in profiles/r01c_vec_occupancy.md (W=128, N=64).
+// Vector-model ensemble kernels: CTA size and resident CTAs per SM.  Their evaluation phase is short, so
+// the serial phases of the stretch move (proposals, accept, split) are about half of a step: many co-resident
+// spectra hide them, and for <= 128 walkers 128-thread CTAs (8 or 6 per SM instead of 4 x 256) keep fewer
+// lanes idle in those phases.  Values from the sweeps in profiles/r01c_vec_occupancy.md and
+// profiles/r01d_vec_kernels.md (W=128, N=64).
 #ifdef BISIP_VEC_MINB
-constexpr int kMinBDias = BISIP_VEC_MINB, kMinBShin = BISIP_VEC_MINB, kMinBCC = BISIP_VEC_MINB;
+constexpr int kMinBVec = BISIP_VEC_MINB;
 #else
-constexpr int kMinBDias = 4, kMinBShin = 4, kMinBCC = 4;
+constexpr int kMinBVec = 4;      // 256-thread CTAs, 64 registers
 #endif
+constexpr int kVecSmallW = 128;  // walkers up to which the 128-thread variant is used
+
+// launch ensemble_kernel<VecEvaluator<Row>> in the shape picked for W walkers; MB128 = CTAs/SM of the
+// 128-thread variant (8 -> 64 registers, 6 -> 80 registers)
+template <class Row, int MB128>
+int launch_vec_ensemble(const EnsembleParams& P, dim3 grid, size_t smem, cudaStream_t st, const char* name);
 
 struct BatchParams {
   bisip_model_desc d;
@@ -184,14 +191,22 @@ size_t batch_smem_bytes(const bisip_model_desc& d) {
 }
 
 template <typename K>
-int launch(K kernel, dim3 grid, size_t smem, cudaStream_t st, const char* name, const void* params_ptr) {
+int launch(K kernel, dim3 grid, size_t smem, cudaStream_t st, const char* name, const void* params_ptr,
+           int threads = kThreads) {
   if ((int)smem > device_smem_optin())
     return fail(BISIP_ERR_UNSUPPORTED, std::string(name) + ": problem does not fit in shared memory");
   BISIP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* args[] = {const_cast<void*>(params_ptr)};
-  BISIP_CUDA(cudaLaunchKernel((const void*)kernel, grid, dim3(kThreads), args, smem, st));
+  BISIP_CUDA(cudaLaunchKernel((const void*)kernel, grid, dim3(threads), args, smem, st));
   g_launches.fetch_add(1);
   return BISIP_OK;
+}
+
+template <class Row, int MB128>
+int launch_vec_ensemble(const EnsembleParams& P, dim3 grid, size_t smem, cudaStream_t st, const char* name) {
+  if (P.W <= kVecSmallW)
+    return launch(ensemble_kernel<VecEvaluator<Row>, MB128, 128>, grid, smem, st, name, &P, 128);
+  return launch(ensemble_kernel<VecEvaluator<Row>, kMinBVec, kThreads>, grid, smem, st, name, &P, kThreads);
 }
 
 template <typename K>
@@ -449,18 +464,18 @@ int bisip_ensemble_run(const bisip_model_desc* desc, int n_spectra, int n_walker
     case BISIP_MODEL_COLECOLE:
       smem += vec_smem_doubles(desc->n_freq, rp, vec_row_consts(*desc)) * 8;
       switch (desc->n_modes) {
-        case 1: return launch(ensemble_kernel<VecEvaluator<ColeColeRowT<1>>, kMinBCC>, grid, smem, st, "ensemble_colecole", &P);
-        case 2: return launch(ensemble_kernel<VecEvaluator<ColeColeRowT<2>>, kMinBCC>, grid, smem, st, "ensemble_colecole", &P);
+        case 1: return launch_vec_ensemble<ColeColeRowT<1>, 8>(P, grid, smem, st, "ensemble_colecole");
+        case 2: return launch_vec_ensemble<ColeColeRowT<2>, 6>(P, grid, smem, st, "ensemble_colecole");
         case 3: return launch(ensemble_kernel<VecEvaluator<ColeColeRowT<3>>, 2>, grid, smem, st, "ensemble_colecole", &P);
         case 4: return launch(ensemble_kernel<VecEvaluator<ColeColeRowT<4>>, 1>, grid, smem, st, "ensemble_colecole", &P);
         default: return launch(ensemble_kernel<VecEvaluator<ColeColeRow>, 1>, grid, smem, st, "ensemble_colecole", &P);
       }
     case BISIP_MODEL_DIAS:
       smem += VecEvaluator<DiasRow>::smem_doubles(*desc, rp) * 8;
-      return launch(ensemble_kernel<VecEvaluator<DiasRow>, kMinBDias>, grid, smem, st, "ensemble_dias", &P);
+      return launch_vec_ensemble<DiasRow, 8>(P, grid, smem, st, "ensemble_dias");
     case BISIP_MODEL_SHIN:
       smem += VecEvaluator<ShinRow>::smem_doubles(*desc, rp) * 8;
-      return launch(ensemble_kernel<VecEvaluator<ShinRow>, kMinBShin>, grid, smem, st, "ensemble_shin", &P);
+      return launch_vec_ensemble<ShinRow, 6>(P, grid, smem, st, "ensemble_shin");
     default: {
       if (use_rc(*desc)) {
         RcPlan plan;

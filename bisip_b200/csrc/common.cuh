@@ -10,7 +10,10 @@
 
 namespace bisip {
 
-constexpr int kThreads = 256;         // CTA size of every hot-path kernel
+#ifndef BISIP_THREADS
+#define BISIP_THREADS 256
+#endif
+constexpr int kThreads = BISIP_THREADS;   // CTA size of every hot-path kernel (developer sweeps: -DBISIP_THREADS=128)
 constexpr int kWarps = kThreads / 32;
 
 // ---------------------------------------------------------------- Philox4x32-10

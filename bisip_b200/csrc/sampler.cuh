@@ -224,7 +224,7 @@ struct RankSide {
       for (; pos < nchunks; ++pos) rank_chunk(kaddr + 16u * pos, ki, r0, r1, r2, r3);
       list_out[(r0 + r1) + (r2 + r3)] = threadIdx.x;
     }
-    for (int i = threadIdx.x + kThreads; i < W; i += kThreads) {   // W > 256: remaining walkers, not interleaved
+    for (int i = threadIdx.x + blockDim.x; i < W; i += blockDim.x) {   // W > CTA size: remaining walkers, not interleaved
       const uint32_t k = keys[i];
       int a = 0, b = 0, c = 0, d = 0;
       for (int ch = 0; ch < nchunks; ++ch) rank_chunk(kaddr + 16u * ch, k, a, b, c, d);
@@ -365,8 +365,10 @@ __device__ __forceinline__ void stagger_start(unsigned long long delay_ns) {
   }
 }
 
-template <class Eval, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) ensemble_kernel(const EnsembleParams P) {
+// NT = CTA size: 256, or 128 for the vector models with <= 128 walkers (twice as many, half as wide
+// CTAs per SM: their serial phases keep fewer lanes idle and interleave better; api.cu picks).
+template <class Eval, int MINB, int NT = kThreads>
+__global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams P) {
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x;
   if (MINB > 1 && !Eval::kClustered) stagger_start(P.stagger_ns);
@@ -390,14 +392,14 @@ __global__ void __launch_bounds__(kThreads, MINB) ensemble_kernel(const Ensemble
   sampler_carve(s, p, W, ndim);
 
   // ---- per-spectrum constants + initial ensemble ---------------------------------------
-  for (int i = tid; i < 2 * ndim; i += kThreads) {
+  for (int i = tid; i < 2 * ndim; i += NT) {
     s.bnd[i] = P.bounds[i];
     s.bkey[i] = ordered_key(P.bounds[i]);
   }
   const double* gc = P.coords + (size_t)b * W * ndim;
-  for (int i = tid; i < W * ndim; i += kThreads) s.coords[i] = gc[i];
-  for (int i = tid; i < W; i += kThreads) s.acc[i] = 0;
-  for (int i = tid; i < rows_pad * ndim; i += kThreads) s.prop[i] = 0.0;
+  for (int i = tid; i < W * ndim; i += NT) s.coords[i] = gc[i];
+  for (int i = tid; i < W; i += NT) s.acc[i] = 0;
+  for (int i = tid; i < rows_pad * ndim; i += NT) s.prop[i] = 0.0;
   ev.init(P.d, P.w + (size_t)b * P.w_stride, P.taus + (size_t)b * P.tau_stride,
           P.log_taus + (size_t)b * P.tau_stride * P.d.n_coef, P.y + (size_t)b * 2 * P.d.n_freq,
           P.yerr + (size_t)b * 2 * P.d.n_freq, s.red);   // ends with __syncthreads()
@@ -409,15 +411,15 @@ __global__ void __launch_bounds__(kThreads, MINB) ensemble_kernel(const Ensemble
   side.begin(s.keys, nullptr, W, 0);
   for (int pass = 0; pass < 2; ++pass) {
     const int off = pass ? H0 : 0, n = pass ? W - H0 : H0;
-    for (int i = tid; i < n * ndim; i += kThreads) s.prop[i] = s.coords[off * ndim + i];
+    for (int i = tid; i < n * ndim; i += NT) s.prop[i] = s.coords[off * ndim + i];
     __syncthreads();
     if (Eval::kNeedsPrepare) {
-      for (int q = tid; q < n; q += kThreads) ev.prepare_row(q, s.prop + q * ndim);
+      for (int q = tid; q < n; q += NT) ev.prepare_row(q, s.prop + q * ndim);
       __syncthreads();
     }
     ev.eval_chi(s.prop, ndim, n, s.chi, side);
     __syncthreads();
-    for (int q = tid; q < n; q += kThreads) {
+    for (int q = tid; q < n; q += NT) {
       const double v = in_bounds(s.prop + q * ndim, s.bnd, ndim) ? -0.5 * (s.chi[q] + llc) : neg_inf();
       if (v != v) flag |= 2;
       s.lp[off + q] = v;
@@ -459,11 +461,11 @@ __global__ void __launch_bounds__(kThreads, MINB) ensemble_kernel(const Ensemble
   };
 
   // prologue: split of step 0 and the draws of its first half-step
-  gen_keys((uint32_t)P.step0, tid, kThreads);
+  gen_keys((uint32_t)P.step0, tid, NT);
   __syncthreads();
   side.begin(s.keys, s.list, W, 0);
   side.finish();
-  gen_proposal_draws((uint32_t)P.step0, 0, tid, kThreads);
+  gen_proposal_draws((uint32_t)P.step0, 0, tid, NT);
   __syncthreads();
 
   PHASE_DECL
@@ -478,7 +480,7 @@ __global__ void __launch_bounds__(kThreads, MINB) ensemble_kernel(const Ensemble
       const double* zzb = s.zz + (size_t)sp * rows_pad;
       // ---- PROPOSE: threads [0,Hs) build q = c_j - (c_j - s_k) zz ; the other threads draw the
       //      acceptance uniforms of this half-step and the FP32 image of the accept threshold ----------
-      for (int idx = tid; idx < 2 * Hs; idx += kThreads) {
+      for (int idx = tid; idx < 2 * Hs; idx += NT) {
         if (idx < Hs) {
           const int q = idx;
           const int j = list[coff + s.partner[q]];
@@ -501,7 +503,7 @@ __global__ void __launch_bounds__(kThreads, MINB) ensemble_kernel(const Ensemble
       PHASE_MARK(2)
       // ---- ACCEPT (threads [0,Hs)) ; the other threads draw the proposal factors of the next
       //      half-step, and after the first half-step the first threads also draw the next step's keys --------
-      for (int idx = tid; idx < 2 * Hs; idx += kThreads) {
+      for (int idx = tid; idx < 2 * Hs; idx += NT) {
         if (idx < Hs) {
           const int q = idx;
           const int k = list[off + q];
@@ -528,12 +530,12 @@ __global__ void __launch_bounds__(kThreads, MINB) ensemble_kernel(const Ensemble
       }
       {
         // spare threads (those beyond the Hs acceptors) prepare the next half-step
-        const int nspare = kThreads - min(Hs, kThreads);
+        const int nspare = NT - min(Hs, NT);
         const bool spare = tid >= Hs;
-        const int worker = spare ? tid - Hs : tid, nworkers = spare ? nspare : kThreads;
+        const int worker = spare ? tid - Hs : tid, nworkers = spare ? nspare : NT;
         if (spare || nspare == 0)
           gen_proposal_draws(sp == 0 ? t : t + 1u, sp ^ 1, worker, nworkers);
-        if (sp == 0 && (!spare || Hs >= kThreads)) gen_keys(t + 1u, tid, min(Hs, kThreads));
+        if (sp == 0 && (!spare || Hs >= NT)) gen_keys(t + 1u, tid, min(Hs, NT));
       }
       __syncthreads();
       PHASE_MARK(3)
@@ -549,11 +551,11 @@ __global__ void __launch_bounds__(kThreads, MINB) ensemble_kernel(const Ensemble
     if (it >= first && (it - first) % P.thin == 0) {
       if (P.chain != nullptr && writer) {
         double* dst = P.chain + ((size_t)b * P.nkeep + kept) * W * ndim;
-        for (int i = tid; i < W * ndim; i += kThreads) __stcs(dst + i, s.coords[i]);
+        for (int i = tid; i < W * ndim; i += NT) __stcs(dst + i, s.coords[i]);
       }
       if (P.logp != nullptr && writer) {
         double* dst = P.logp + ((size_t)b * P.nkeep + kept) * W;
-        for (int i = tid; i < W; i += kThreads) __stcs(dst + i, s.lp[i]);
+        for (int i = tid; i < W; i += NT) __stcs(dst + i, s.lp[i]);
       }
       ++kept;
     }
@@ -563,8 +565,8 @@ __global__ void __launch_bounds__(kThreads, MINB) ensemble_kernel(const Ensemble
   // ---- final state ------------------------------------------------------------------------------
   if (writer) {
     double* gco = P.coords + (size_t)b * W * ndim;
-    for (int i = tid; i < W * ndim; i += kThreads) gco[i] = s.coords[i];
-    for (int i = tid; i < W; i += kThreads) {
+    for (int i = tid; i < W * ndim; i += NT) gco[i] = s.coords[i];
+    for (int i = tid; i < W; i += NT) {
       if (P.lp) P.lp[(size_t)b * W + i] = s.lp[i];
       if (P.accepted) P.accepted[(size_t)b * W + i] = s.acc[i];
     }
