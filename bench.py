@@ -75,7 +75,7 @@ def _ref_worker(args):
 def reference_sample(zn, zn_err, w, cores, walkers=WALKERS, nsteps=None, pool=None):
     """Bounded sample: `cores` spectra (one per process) x walkers x nsteps.  Returns evals/s."""
     import multiprocessing as mp
-    nsteps = nsteps or env_int("BISIP_BENCH_REF_STEPS", 100)
+    nsteps = nsteps or env_int("BISIP_BENCH_REF_STEPS", 300)
     jobs = [(b, zn[b], zn_err[b], w, walkers, nsteps) for b in range(cores)]
     own = pool is None
     if own:
@@ -296,11 +296,12 @@ def run_gpu(args):
         k_ms = float(np.mean(kern_ms))
         flops_launch = FLOP_PER_EVAL * float(B) * WALKERS * (NSTEPS + 1)       # +1: log-prob of p0
         achieved = flops_launch / (k_ms * 1e-3) / 1e12
-        traffic = None
+        traffic = traffic_src = None
         summ = os.path.join(ROOT, "profiles", "ncu_summary.json")
-        if os.path.exists(summ):
+        if os.path.exists(summ) and B == 12500:          # the committed ncu figure is for the default shard size
             try:
-                traffic = json.load(open(summ)).get("ensemble_decomp", {}).get("dram_bytes_per_launch_at_bench_size")
+                e = json.load(open(summ)).get("ensemble_decomp", {})
+                traffic, traffic_src = e.get("dram_bytes_per_launch_at_bench_size"), e.get("dram_bytes_source")
             except Exception:
                 traffic = None
         # CPU baseline (bounded sample of the same spectra, all host cores)
@@ -321,7 +322,10 @@ def run_gpu(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "ensemble_kernel<DecompEvaluator<4>> (bisip_ensemble_run)",
                          "achieved": achieved, "peak": peak_sust, "unit": "TFLOP/s", "frac": achieved / peak_sust,
-                         "traffic": traffic, "peak_source": peak_src, "peak_burst": peak_burst,
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes": float(B) * (nk * WALKERS * inv.ndim * 8 + 2 * WALKERS * inv.ndim * 8
+                                                          + WALKERS * 12 + 4 * N_FREQ * 8 + 4),
+                         "peak_source": peak_src, "peak_burst": peak_burst,
                          "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_step,
                          "algorithmic_flop_per_eval": FLOP_PER_EVAL},
             "cpu_baseline": {"value": cpu_v, "unit": "evals/s", "cores": min(cores, B), "kind": "reference", "sample": cpu_sample,

@@ -95,17 +95,53 @@ def main():
                          pct_of_samples=round(100 * g["samples"] / tot, 2),
                          **{k: round(100 * g[k] / tot, 2) for k in cols})
                     for g in regions if g["samples"] > 0.005 * tot]
+    # ---- executed warp instructions by class (issue-slot budget) ------------------------------------
+    def cls(text):
+        t = text.split()
+        if not t:
+            return "other"
+        op = (t[1] if t[0].startswith("@") and len(t) > 1 else t[0]).split(".")[0]
+        if op == "DMMA":
+            return "dmma"
+        if op in ("DFMA", "DMUL", "DADD", "DSETP"):
+            return "fp64"
+        if op in ("FFMA", "FMUL", "FADD", "FSETP", "FSEL", "FMNMX", "HMMA"):
+            return "fp32"
+        if op == "MUFU":
+            return "mufu"
+        if op in ("I2F", "F2I", "F2F", "I2FP", "F2FP"):
+            return "convert"
+        if op in ("LDS", "STS", "LDSM", "ATOMS"):
+            return "shared_mem"
+        if op in ("LDG", "STG", "LD", "ST", "LDL", "STL", "ATOMG", "RED", "LDC", "LDCU"):
+            return "other_mem"
+        if op in ("BAR", "BSSY", "BSYNC", "BRA", "EXIT", "CALL", "RET", "WARPSYNC", "NANOSLEEP"):
+            return "control"
+        if op in ("SHFL", "VOTE", "MATCH"):
+            return "shuffle"
+        return "integer"
+    mix, tot_ex = {}, 0
+    for r in data:
+        ex = int(r[iex])
+        tot_ex += ex
+        k = cls(r[isrc])
+        mix[k] = mix.get(k, 0) + ex
+    m["warp_instructions"] = tot_ex
+    m["instruction_mix_pct"] = {k: round(100.0 * v / max(tot_ex, 1), 2) for k, v in sorted(mix.items(), key=lambda kv: -kv[1])}
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     json.dump(m, open(a.out + ".json", "w"), indent=1)
     with open(a.out + ".md", "w") as f:
         f.write(f"# ncu summary — {a.name}\n\n`{m['kernel']}`  (report {m['report']}; {a.note})\n\n")
         f.write("| metric | value |\n|---|---|\n")
         for k, v in m.items():
-            if k not in ("regions", "stall_per_issue", "kernel", "report", "note"):
+            if k not in ("regions", "stall_per_issue", "kernel", "report", "note", "instruction_mix_pct"):
                 f.write(f"| {k} | {v:.6g} |\n" if isinstance(v, float) else f"| {k} | {v} |\n")
         f.write("\n## warp stall reasons (warps stalled per issue-active cycle)\n\n| reason | ratio |\n|---|---|\n")
         for k, v in sorted(m.get("stall_per_issue", {}).items(), key=lambda kv: -kv[1]):
             f.write(f"| {k} | {v:.3f} |\n")
+        f.write("\n## executed warp instructions by class (% of all)\n\n| class | % |\n|---|---|\n")
+        for k, v in m["instruction_mix_pct"].items():
+            f.write(f"| {k} | {v} |\n")
         f.write("\n## SASS regions (consecutive instructions with equal execution count), % of all warp samples\n\n")
         f.write("| instrs | exec/instr | DMMA instrs | samples % | barrier % | math-pipe % | wait % | short-sb % |\n|---|---|---|---|---|---|---|---|\n")
         for g in m["regions"]:
