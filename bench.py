@@ -109,7 +109,7 @@ def synthetic_cpu(n):
         prob = oracle.Problem('decomp', ww, np.zeros((2, len(ww))), np.ones((2, len(ww))),
                               np.zeros((2, theta.shape[1])), taus=taus, log_taus=log_taus, c_exp=1.0)
         return prob.forward(theta)
-    return synthetic.make('decomp', 0, n, fwd, N=N_FREQ, poly_deg=POLY_DEG)
+    return synthetic.make('decomp', 0, n, fwd, N=N_FREQ, poly_deg=POLY_DEG, n_tau=N_TAU)
 
 
 def run_reference(args):
@@ -211,7 +211,7 @@ def run_gpu(args):
     def cuda_forward(theta, w):
         th = _lib.dev_f64(theta[:, None, :], dev)
         return engine.forward(probe._spec(), th, _lib.dev_f64(w, dev))[:, 0].cpu().numpy()
-    syn = synthetic.make('decomp', b0, b0 + B, cuda_forward, N=N_FREQ, poly_deg=POLY_DEG)
+    syn = synthetic.make('decomp', b0, b0 + B, cuda_forward, N=N_FREQ, poly_deg=POLY_DEG, n_tau=N_TAU)
     zn_h = torch.from_numpy(syn['zn']).pin_memory()
     ze_h = torch.from_numpy(syn['zn_err']).pin_memory()
     inv = BatchInversion('decomp', syn['w'], zn_h, ze_h, nwalkers=WALKERS, nsteps=NSTEPS, poly_deg=POLY_DEG,

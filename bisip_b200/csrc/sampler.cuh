@@ -28,7 +28,7 @@ namespace bisip {
 #define PHASE_MARK(i) { long long n_ = clock64(); ph_[i] += n_ - ph_t_; ph_t_ = n_; }
 #define PHASE_PRINT if (blockIdx.x == 0 && threadIdx.x == 0) printf("phase cycles/step: split %.0f  propose %.0f  eval %.0f  accept %.0f  store %.0f\n", \
     (double)ph_[0] / P.nsteps, (double)ph_[1] / P.nsteps, (double)ph_[2] / P.nsteps, (double)ph_[3] / P.nsteps, (double)ph_[4] / P.nsteps); \
-  if (blockIdx.x == 0 && threadIdx.x == 0) printf("fine (thread 0) cycles/step: %.0f %.0f %.0f %.0f %.0f %.0f\n", (double)ph_[6] / P.nsteps, (double)ph_[7] / P.nsteps, (double)ph_[8] / P.nsteps, (double)ph_[9] / P.nsteps, (double)ph_[10] / P.nsteps, (double)ph_[11] / P.nsteps);
+  if (blockIdx.x == 0 && threadIdx.x == 0) printf("fine (thread 0) cycles/step: propose-body %.0f  propose-barrier %.0f  eval-body %.0f  eval-barrier %.0f  accept-body %.0f  accept-tail(keys) %.0f ; %.0f\n", (double)ph_[6] / P.nsteps, (double)ph_[7] / P.nsteps, (double)ph_[8] / P.nsteps, (double)ph_[9] / P.nsteps, (double)ph_[10] / P.nsteps, (double)ph_[11] / P.nsteps, 0.0);
 #else
 #define FINE_START
 #define FINE_MARK(i)
@@ -480,6 +480,7 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
       const double* zzb = s.zz + (size_t)sp * rows_pad;
       // ---- PROPOSE: threads [0,Hs) build q = c_j - (c_j - s_k) zz ; the other threads draw the
       //      acceptance uniforms of this half-step and the FP32 image of the accept threshold ----------
+      FINE_START
       for (int idx = tid; idx < 2 * Hs; idx += NT) {
         if (idx < Hs) {
           const int q = idx;
@@ -495,11 +496,15 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
           s.lf[q] = (float)(ndim - 1) * logf((float)zzb[q]) - logf((float)u2);
         }
       }
+      FINE_MARK(6)
       __syncthreads();
+      FINE_MARK(7)
       PHASE_MARK(1)
       // ---- EVAL: fused forward + chi^2 of all proposals ----------------------------------------------
       ev.eval_chi(s.prop, ndim, Hs, s.chi, side);
+      FINE_MARK(8)
       __syncthreads();
+      FINE_MARK(9)
       PHASE_MARK(2)
       // ---- ACCEPT (threads [0,Hs)) ; the other threads draw the proposal factors of the next
       //      half-step, and after the first half-step the first threads also draw the next step's keys --------
@@ -528,6 +533,7 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
           }
         }
       }
+      FINE_MARK(10)
       {
         // spare threads (those beyond the Hs acceptors) prepare the next half-step
         const int nspare = NT - min(Hs, NT);
@@ -537,6 +543,7 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
           gen_proposal_draws(sp == 0 ? t : t + 1u, sp ^ 1, worker, nworkers);
         if (sp == 0 && (!spare || Hs >= NT)) gen_keys(t + 1u, tid, min(Hs, NT));
       }
+      FINE_MARK(11)
       __syncthreads();
       PHASE_MARK(3)
     }

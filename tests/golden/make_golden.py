@@ -148,7 +148,8 @@ def main():
     for model, kw in syn_cases:
         tag = f"syn_{model}" + (f"_s{kw['n_tau']}" if 'n_tau' in kw else '')
         f, taus, log_taus = ref_forward(model, **kw)
-        syn = synthetic.make(model, 0, 4, f, N=N, poly_deg=kw.get('poly_deg', 4), n_modes=kw.get('n_modes', 1))
+        syn = synthetic.make(model, 0, 4, f, N=N, poly_deg=kw.get('poly_deg', 4), n_modes=kw.get('n_modes', 1),
+                             n_tau=kw.get('n_tau'))
         _, bounds = default_bounds(model, kw.get('poly_deg', 4), kw.get('n_modes', 1))
         fl[f'{tag}/zn'], fl[f'{tag}/zn_err'] = syn['zn'], syn['zn_err']
         fl[f'{tag}/theta_true'] = syn['theta_true']

@@ -178,7 +178,7 @@ def test_synthetic_generator_is_shard_independent():
     np.testing.assert_array_equal(a['zn'][3:], b['zn'])
     np.testing.assert_array_equal(a['theta_true'][3:], b['theta_true'])
     lo, hi = synthetic.true_box('decomp', 4)
-    assert lo[0] == 0.95 and hi[1] == 0.02 and a['zn'].shape == (6, 2, 16)
+    assert lo[0] == 0.95 and hi[0] == 1.05 and a['zn'].shape == (6, 2, 16)
     assert np.allclose(np.max(np.hypot(a['zn'][:, 0], a['zn'][:, 1]), axis=1), 1.0)
 
 

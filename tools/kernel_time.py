@@ -20,7 +20,7 @@ _, w = synthetic.frequencies(a.N)
 kw = dict(poly_deg=a.P, n_tau=a.S, c_exp=a.c_exp, precision=a.precision) if a.model == "decomp" else (dict(n_modes=a.K) if a.model == "colecole" else {})
 probe = BatchInversion(a.model, w, np.zeros((1, 2, a.N)), np.ones((1, 2, a.N)), device=dev, **kw)
 fwd = lambda th, ww: engine.forward(probe._spec(), _lib.dev_f64(th[:, None, :], dev), _lib.dev_f64(ww, dev))[:, 0].cpu().numpy()
-syn = synthetic.make(a.model, 0, a.B, fwd, N=a.N, poly_deg=a.P, n_modes=a.K)
+syn = synthetic.make(a.model, 0, a.B, fwd, N=a.N, poly_deg=a.P, n_modes=a.K, n_tau=a.S)
 inv = BatchInversion(a.model, w, syn["zn"], syn["zn_err"], nwalkers=a.W, nsteps=a.T, seed=1, device=dev, **kw)
 p0 = _lib.dev_f64(inv.draw_p0(0, a.B), dev)
 y, ye = _lib.dev_f64(syn["zn"], dev), _lib.dev_f64(syn["zn_err"], dev)
