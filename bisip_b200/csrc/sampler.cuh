@@ -66,7 +66,7 @@ struct SamplerSmem {
   double* bnd;     // [2][ndim]
   double* red;     // [kWarps]
   long long* bkey; // [2][ndim] ordered-integer image of bnd
-  float* lf;       // [rows_pad]     (ndim-1) ln zz - ln u in FP32 (accept filter)
+  double* lf;      // [rows_pad]     (ndim-1) ln zz - ln u, evaluated in FP32 (accept filter), stored widened
   uint32_t* keys;  // [Wpad4]        shuffle keys of the NEXT step
   int* list;       // [2][W]         walker at rank, double-buffered by step parity
   int* acc;        // [W]
@@ -78,8 +78,8 @@ __host__ __device__ inline int sampler_rows_pad(int W) { return ceil_div((W + 1)
 
 __host__ __device__ inline size_t sampler_smem_bytes(int W, int ndim) {
   const int rp = sampler_rows_pad(W);
-  size_t dbl = (size_t)W * ndim + W + (size_t)rp * ndim + rp + 2 * rp + rp + 4 * ndim + kWarps;
-  size_t words = (size_t)rp + (W + 4) + 2 * W + W + rp + rp;
+  size_t dbl = (size_t)W * ndim + W + (size_t)rp * ndim + rp + 2 * rp + rp + rp + 4 * ndim + kWarps;
+  size_t words = (size_t)(W + 4) + 2 * W + W + rp + rp;
   return dbl * 8 + words * 4 + 32;
 }
 
@@ -91,12 +91,12 @@ __device__ inline void sampler_carve(SamplerSmem& s, double* base, int W, int nd
   s.chi = base; base += rp;
   s.zz = base; base += 2 * rp;
   s.u2 = base; base += rp;
+  s.lf = base; base += rp;
   s.bnd = base; base += 2 * ndim;
   s.red = base; base += kWarps;
   s.bkey = reinterpret_cast<long long*>(base); base += 2 * ndim;
   s.keys = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(base) + 15) & ~uintptr_t(15));   // LDS.128
-  s.lf = reinterpret_cast<float*>(s.keys + ((W + 3) & ~3));
-  s.list = reinterpret_cast<int*>(s.lf + rp);
+  s.list = reinterpret_cast<int*>(s.keys + ((W + 3) & ~3));
   s.acc = s.list + 2 * W;
   s.inb = s.acc + W;
   s.partner = s.inb + rp;
@@ -127,34 +127,75 @@ __device__ __forceinline__ bool in_bounds_keys(const double* th, const long long
 }
 
 // ndim is a run-time value (1+3K, 5, 6, 2+poly_deg): a plain loop over it serialises its shared-memory
-// loads (one ~30-cycle round trip per dimension).  These helpers unroll the first kDimUnroll
-// dimensions under a predicate so all loads of a proposal are in flight together.
+// loads (one ~30-cycle round trip per dimension).  The proposal is therefore built by a fully unrolled
+// body picked by a switch on ndim (2..9 cover poly_deg 0..7, Dias, Shin and 1-2 Cole-Cole modes), so all
+// loads of a proposal are in flight together and no instruction is spent on absent dimensions — each FP64
+// operation here queues behind the co-resident CTA's tensor-pipe stream.
 constexpr int kDimUnroll = 8;
 
 // q = c - (c - s) * zz (explicitly unfused, like the oracle) -> dst ; returns the strict-prior flag
+template <int ND>
+__device__ __forceinline__ bool propose_and_check_n(const double* __restrict__ cj, const double* __restrict__ sk,
+                                                    double zz, double* __restrict__ dst,
+                                                    const long long* __restrict__ bkey) {
+  double c[ND], x[ND];
+  long long lo[ND], hi[ND];
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    c[d] = cj[d];
+    x[d] = sk[d];
+    lo[d] = bkey[d];
+    hi[d] = bkey[ND + d];
+  }
+  bool ok = true;
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    const double v = __dsub_rn(c[d], __dmul_rn(__dsub_rn(c[d], x[d]), zz));
+    const long long k = ordered_key(v);
+    dst[d] = v;
+    ok = ok & (lo[d] < k) & (k < hi[d]);
+  }
+  return ok;
+}
+
 __device__ __forceinline__ bool propose_and_check(const double* __restrict__ cj, const double* __restrict__ sk,
                                                   double zz, double* __restrict__ dst, const long long* __restrict__ bkey,
                                                   int ndim) {
-  bool ok = true;
-#pragma unroll
-  for (int d = 0; d < kDimUnroll; ++d) {
-    const int dd = d < ndim ? d : 0;                 // always a valid address: loads need no predicate
-    const double c = cj[dd], x = sk[dd];
-    const long long lo = bkey[dd], hi = bkey[ndim + dd];
-    const double v = __dsub_rn(c, __dmul_rn(__dsub_rn(c, x), zz));
-    const long long k = ordered_key(v);
-    if (d < ndim) {
-      dst[d] = v;
-      ok = ok & (lo < k) & (k < hi);
-    }
+  switch (ndim) {
+    case 2: return propose_and_check_n<2>(cj, sk, zz, dst, bkey);
+    case 3: return propose_and_check_n<3>(cj, sk, zz, dst, bkey);
+    case 4: return propose_and_check_n<4>(cj, sk, zz, dst, bkey);
+    case 5: return propose_and_check_n<5>(cj, sk, zz, dst, bkey);
+    case 6: return propose_and_check_n<6>(cj, sk, zz, dst, bkey);
+    case 7: return propose_and_check_n<7>(cj, sk, zz, dst, bkey);
+    case 8: return propose_and_check_n<8>(cj, sk, zz, dst, bkey);
+    case 9: return propose_and_check_n<9>(cj, sk, zz, dst, bkey);
+    default: break;
   }
-  for (int d = kDimUnroll; d < ndim; ++d) {
+  bool ok = true;
+  for (int d = 0; d < ndim; ++d) {
     const double v = __dsub_rn(cj[d], __dmul_rn(__dsub_rn(cj[d], sk[d]), zz));
     dst[d] = v;
     const long long k = ordered_key(v);
     ok = ok & (bkey[d] < k) & (k < bkey[ndim + d]);
   }
   return ok;
+}
+
+// Accept filter on the integer pipe.  est = (lp' - lp) + lf is the FP32-logarithm image of emcee's
+// (ndim-1) ln zz + lp' - lp - ln u, whose error is < 1e-5 from the logarithms plus the FP64 rounding of the two
+// log-probabilities (<= 2^-52 (|lp'| + |lp|)).  The FP64 decision is therefore already determined whenever
+// |est| >= 2^-12 and |est| >= 2^-46 max(|lp'|, |lp|); both are comparisons of biased exponents.  NaN (inf - inf)
+// is "determined" too: emcee's `nan > x` is False.  Returns true when determined and sets `accept`.
+__device__ __forceinline__ bool accept_filter(double est, double lpn, double lpo, bool& accept) {
+  const int he = __double2hiint(est);
+  const unsigned ae = (unsigned)he & 0x7fffffffu;
+  const unsigned e_est = ae >> 20;
+  const unsigned e_n = ((unsigned)__double2hiint(lpn) >> 20) & 0x7ffu, e_o = ((unsigned)__double2hiint(lpo) >> 20) & 0x7ffu;
+  const unsigned emax = e_n > e_o ? e_n : e_o;
+  const bool is_nan = ae > 0x7ff00000u || (ae == 0x7ff00000u && __double2loint(est) != 0);
+  accept = (he >= 0) && !is_nan;
+  return e_est >= 1011u && e_est + 46u >= emax;
 }
 
 __device__ __forceinline__ void copy_dims(double* __restrict__ dst, const double* __restrict__ src, int ndim) {
@@ -493,7 +534,7 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
           const u32x4 r = philox4x32_10((uint32_t)q, t, spec, (uint32_t)(2 + 2 * sp), k0, k1);
           const double u2 = u53(r.x, r.y);
           s.u2[q] = u2;
-          s.lf[q] = (float)(ndim - 1) * logf((float)zzb[q]) - logf((float)u2);
+          s.lf[q] = (double)((float)(ndim - 1) * logf((float)zzb[q]) - logf((float)u2));
         }
       }
       FINE_MARK(6)
@@ -518,11 +559,9 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
           // emcee: accept iff (ndim-1) ln zz + lp' - lp > ln u.  The logarithms were taken in FP32
           // (|error| < 1e-5): unless the margin is below the threshold the FP64 decision is already
           // determined; otherwise (about 1 proposal in 10^4) it is recomputed in FP64 as the oracle does.
-          const double est = __dsub_rn(lpn, lpo) + (double)s.lf[q];
+          const double est = __dsub_rn(lpn, lpo) + s.lf[q];
           bool accept;
-          if (fabs(est) > fma(1e-15, fabs(lpn) + fabs(lpo), 1e-4)) {
-            accept = est > 0.0;
-          } else {
+          if (!accept_filter(est, lpn, lpo, accept)) {
             const double lnpdiff = __dsub_rn(__dadd_rn(__dmul_rn((double)(ndim - 1), log(zzb[q])), lpn), lpo);
             accept = lnpdiff > log(s.u2[q]);
           }
