@@ -243,13 +243,17 @@ size_t rc_eval_doubles(const bisip_model_desc& d, int rows_pad, int cs) {
   }
 }
 int plan_rc(const bisip_model_desc& d, size_t other_bytes, int rows_pad, RcPlan* out) {
+  // Smallest cluster first; for a given cluster size two CTAs per SM if they fit, else one.  A wider cluster is
+  // worse than a lower occupancy: every CTA of a cluster repeats the sampler's serial phases, and measured on
+  // B200 (W=256, N=64) a 2-CTA cluster at one CTA/SM runs n_tau=256 at 24.7 TFLOP/s while 4-CTA clusters at two
+  // CTAs/SM reach 20.6-22.0 TFLOP/s for n_tau=160..240 (profiles/r01e_cluster_plan.md).
   const size_t two = 113 * 1024, one = (size_t)device_smem_optin();
   const int cands[3] = {1, 2, 4};
-  for (int pass = 0; pass < 2; ++pass)
-    for (int i = 0; i < 3; ++i) {
-      const size_t smem = other_bytes + rc_eval_doubles(d, rows_pad, cands[i]) * 8;
-      if (smem <= (pass == 0 ? two : one)) { *out = {cands[i], pass == 0, smem}; return BISIP_OK; }
-    }
+  for (int i = 0; i < 3; ++i) {
+    const size_t smem = other_bytes + rc_eval_doubles(d, rows_pad, cands[i]) * 8;
+    if (smem <= two) { *out = {cands[i], true, smem}; return BISIP_OK; }
+    if (smem <= one) { *out = {cands[i], false, smem}; return BISIP_OK; }
+  }
   return fail(BISIP_ERR_UNSUPPORTED, "Decomp: n_tau x n_freq too large for a 4-CTA cluster's shared memory");
 }
 // the clustered ("rc") layout serves every reduced-precision run and every FP64 run with n_tau > 64
