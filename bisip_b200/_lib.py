@@ -14,8 +14,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BISIP_B200_LIB", os.path.join(_HERE, "csrc", "libbisip_b200.so"))   # env: developer builds
 
 MODEL_COLECOLE, MODEL_DIAS, MODEL_SHIN, MODEL_DECOMP = 0, 1, 2, 3
-PREC_FP64, PREC_TF32, PREC_3XTF32 = 0, 1, 2
-PRECISIONS = {"fp64": PREC_FP64, "tf32": PREC_TF32, "3xtf32": PREC_3XTF32}
+PREC_FP64, PREC_TF32, PREC_3XTF32, PREC_TF32_MMA, PREC_3XTF32_MMA = 0, 1, 2, 3, 4
+PRECISIONS = {"fp64": PREC_FP64, "tf32": PREC_TF32, "3xtf32": PREC_3XTF32,
+              "tf32-mma": PREC_TF32_MMA, "3xtf32-mma": PREC_3XTF32_MMA}
 MAX_PCT = 16
 
 EXPORTS = ("bisip_abi_version", "bisip_last_error", "bisip_launch_count", "bisip_forward",

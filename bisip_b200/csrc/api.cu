@@ -50,7 +50,7 @@ int check_desc(const bisip_model_desc* d) {
       if (d->n_tau <= 0 || d->n_coef <= 0) return fail(BISIP_ERR_BAD_ARG, "Decomp n_tau/n_coef must be positive");
       if (d->ndim != 1 + d->n_coef) return fail(BISIP_ERR_BAD_ARG, "Decomp ndim != 1+n_coef");
       if (d->n_coef > 8) return fail(BISIP_ERR_UNSUPPORTED, "Decomp poly_deg > 7 not supported");
-      if (d->precision != BISIP_PREC_FP64 && d->precision != BISIP_PREC_TF32 && d->precision != BISIP_PREC_3XTF32)
+      if (d->precision < BISIP_PREC_FP64 || d->precision > BISIP_PREC_3XTF32_MMA)
         return fail(BISIP_ERR_BAD_ARG, "unknown precision");
       break;
     default:
@@ -235,10 +235,18 @@ int launch_cluster(K kernel, dim3 grid, int cluster, size_t smem, cudaStream_t s
 
 // Large tau grids: pick the cluster size (column split) so that K fits; prefer two CTAs per SM.
 struct RcPlan { int cs; bool two_per_sm; size_t smem; };
+// 0 = FP64, 1 = TF32, 3 = 3xTF32 (operand planes per product)
+int prec_planes(int precision) {
+  switch (precision) {
+    case BISIP_PREC_TF32: case BISIP_PREC_TF32_MMA: return 1;
+    case BISIP_PREC_3XTF32: case BISIP_PREC_3XTF32_MMA: return 3;
+    default: return 0;
+  }
+}
 size_t rc_eval_doubles(const bisip_model_desc& d, int rows_pad, int cs) {
-  switch (d.precision) {
-    case BISIP_PREC_TF32: return DecompTF32Evaluator<1>::smem_doubles(d, rows_pad, cs);
-    case BISIP_PREC_3XTF32: return DecompTF32Evaluator<3>::smem_doubles(d, rows_pad, cs);
+  switch (prec_planes(d.precision)) {
+    case 1: return DecompTF32Evaluator<1>::smem_doubles(d, rows_pad, cs);
+    case 3: return DecompTF32Evaluator<3>::smem_doubles(d, rows_pad, cs);
     default: return DecompRCEvaluator::smem_doubles(d, rows_pad, cs);
   }
 }
@@ -256,9 +264,30 @@ int plan_rc(const bisip_model_desc& d, size_t other_bytes, int rows_pad, RcPlan*
   }
   return fail(BISIP_ERR_UNSUPPORTED, "Decomp: n_tau x n_freq too large for a 4-CTA cluster's shared memory");
 }
-// the clustered ("rc") layout serves every reduced-precision run and every FP64 run with n_tau > 64
+// the clustered ("rc") layout serves every mma.sync reduced-precision run and every FP64 run with n_tau > 64
 bool use_rc(const bisip_model_desc& d) {
   return d.model == BISIP_MODEL_DECOMP && (d.n_tau > 64 || d.precision != BISIP_PREC_FP64);
+}
+
+// tcgen05 path (decomp_umma.cuh): BISIP_PREC_TF32 / _3XTF32 whenever one M = 128 tile holds a half-step
+// (rows <= 128), 2N <= 128 columns, and the B planes fit in shared memory next to `other_bytes`.
+// n_tau <= 64: 256 tensor-memory columns per CTA, two CTAs per SM — the request is padded so that a third CTA
+// (which would spin in tcgen05.alloc) never becomes resident.  n_tau > 64: 512 columns, so the request is padded
+// past half an SM's shared memory and exactly one CTA is resident.
+struct UmmaPlan { bool ok; bool two_per_sm; size_t smem; };
+UmmaPlan plan_umma(const bisip_model_desc& d, size_t other_bytes, int rows) {
+  UmmaPlan pl{false, false, 0};
+  const int planes = prec_planes(d.precision);
+  if (d.model != BISIP_MODEL_DECOMP || (d.precision != BISIP_PREC_TF32 && d.precision != BISIP_PREC_3XTF32)) return pl;
+  if (rows > kUmmaRows || !DecompUmmaShape::fits(d.n_freq, d.n_tau)) return pl;
+  const DecompUmmaShape sh(d.n_freq, d.n_tau, d.n_coef);
+  size_t smem = other_bytes + decomp_umma_smem_doubles(sh, planes) * 8;
+  if (smem > (size_t)device_smem_optin()) return pl;
+  pl.ok = true;
+  pl.two_per_sm = sh.nchunks == 1 && smem <= 113 * 1024;
+  const size_t floor_bytes = pl.two_per_sm ? 77 * 1024 : 116 * 1024;
+  pl.smem = smem < floor_bytes ? floor_bytes : smem;
+  return pl;
 }
 
 // uniform access to the three clustered evaluators for the batch kernel
@@ -326,8 +355,54 @@ __global__ void __launch_bounds__(kThreads) decomp_rc_batch_kernel(const BatchPa
   if (cs > 1) cluster.sync();
 }
 
+// Batched forward / log-probability on the tcgen05 path: grid (chunks, B), 128 theta rows per tile.
+template <int PREC, bool WANT_Z>
+__global__ void __launch_bounds__(kThreads) decomp_umma_batch_kernel(const BatchParams P) {
+  extern __shared__ __align__(16) double smem[];
+  const int b = blockIdx.y, ndim = P.d.ndim, N = P.d.n_freq;
+  DecompUmmaShape sh(P.d.n_freq, P.d.n_tau, P.d.n_coef);
+  DecompUmmaSmem s;
+  double* p = decomp_umma_carve<PREC>(s, smem, sh);
+  double* prop = p; p += kRows * ndim;
+  double* chi = p; p += kRows;
+  double* bnd = p; p += 2 * ndim;
+  double* red = p;
+  if (!WANT_Z) for (int i = threadIdx.x; i < 2 * ndim; i += kThreads) bnd[i] = P.bounds[i];
+  decomp_umma_init<PREC>(s, sh, P.d.c_exp, P.w + (size_t)b * P.w_stride, P.taus + (size_t)b * P.tau_stride,
+                         P.log_taus + (size_t)b * P.tau_stride * P.d.n_coef,
+                         WANT_Z ? nullptr : P.y + (size_t)b * 2 * N, WANT_Z ? nullptr : P.yerr + (size_t)b * 2 * N, red);
+  for (int r0 = blockIdx.x * kRows; r0 < P.n_theta; r0 += gridDim.x * kRows) {
+    const int n = min(kRows, P.n_theta - r0);
+    const double* th = P.theta + ((size_t)b * P.n_theta + r0) * ndim;
+    for (int i = threadIdx.x; i < kRows * ndim; i += kThreads) prop[i] = (i < n * ndim) ? th[i] : 0.0;
+    __syncthreads();
+    decomp_umma_eval<PREC, WANT_Z>(s, sh, prop, ndim, n, chi,
+                                   WANT_Z ? P.Z + ((size_t)b * P.n_theta + r0) * 2 * N : nullptr);
+    __syncthreads();
+    if (!WANT_Z)
+      for (int q = threadIdx.x; q < n; q += kThreads)
+        P.lp[(size_t)b * P.n_theta + r0 + q] =
+            in_bounds(prop + q * ndim, bnd, ndim) ? -0.5 * (chi[q] + s.llconst) : neg_inf();
+    __syncthreads();
+  }
+  decomp_umma_release(s, sh);
+}
+
 template <bool WANT_Z>
 int run_batch(const BatchParams& P, cudaStream_t st) {
+  {
+    const size_t other = ((size_t)kRows * P.d.ndim + kRows + 2 * P.d.ndim + kWarps) * 8;
+    const UmmaPlan up = plan_umma(P.d, other, kRows);
+    if (up.ok) {
+      int chunks = ceil_div(P.n_theta, kRows);
+      const int cap = max(1, (148 * 2) / max(1, P.B));
+      if (chunks > cap) chunks = cap;
+      const dim3 g(chunks, P.B);
+      if (prec_planes(P.d.precision) == 3)
+        return launch(decomp_umma_batch_kernel<3, WANT_Z>, g, up.smem, st, "decomp_umma_3xtf32_batch", &P);
+      return launch(decomp_umma_batch_kernel<1, WANT_Z>, g, up.smem, st, "decomp_umma_tf32_batch", &P);
+    }
+  }
   if (use_rc(P.d)) {
     RcPlan plan;
     const size_t other = ((size_t)kRows * P.d.ndim + kRows + 2 * P.d.ndim + kWarps) * 8;
@@ -336,9 +411,9 @@ int run_batch(const BatchParams& P, cudaStream_t st) {
     const int cap = max(1, (148 * 2) / max(1, P.B * plan.cs));
     if (chunks > cap) chunks = cap;
     const dim3 g(chunks * plan.cs, P.B);
-    switch (P.d.precision) {
-      case BISIP_PREC_TF32: return launch_cluster(decomp_rc_batch_kernel<1, WANT_Z>, g, plan.cs, plan.smem, st, "decomp_tf32_batch", &P);
-      case BISIP_PREC_3XTF32: return launch_cluster(decomp_rc_batch_kernel<3, WANT_Z>, g, plan.cs, plan.smem, st, "decomp_3xtf32_batch", &P);
+    switch (prec_planes(P.d.precision)) {
+      case 1: return launch_cluster(decomp_rc_batch_kernel<1, WANT_Z>, g, plan.cs, plan.smem, st, "decomp_tf32_batch", &P);
+      case 3: return launch_cluster(decomp_rc_batch_kernel<3, WANT_Z>, g, plan.cs, plan.smem, st, "decomp_3xtf32_batch", &P);
       default: return launch_cluster(decomp_rc_batch_kernel<0, WANT_Z>, g, plan.cs, plan.smem, st, "decomp_rc_batch", &P);
     }
   }
@@ -481,6 +556,17 @@ int bisip_ensemble_run(const bisip_model_desc* desc, int n_spectra, int n_walker
       smem += VecEvaluator<ShinRow>::smem_doubles(*desc, rp) * 8;
       return launch_vec_ensemble<ShinRow, 6>(P, grid, smem, st, "ensemble_shin");
     default: {
+      {
+        const UmmaPlan up = plan_umma(*desc, smem, (n_walkers + 1) / 2);
+        if (up.ok) {
+          const bool x3 = prec_planes(desc->precision) == 3;
+          if (up.two_per_sm)
+            return x3 ? launch(ensemble_kernel<DecompUmmaEvaluator<3>, 2>, grid, up.smem, st, "ensemble_decomp_umma_3xtf32", &P)
+                      : launch(ensemble_kernel<DecompUmmaEvaluator<1>, 2>, grid, up.smem, st, "ensemble_decomp_umma_tf32", &P);
+          return x3 ? launch(ensemble_kernel<DecompUmmaEvaluator<3>, 1>, grid, up.smem, st, "ensemble_decomp_umma_3xtf32", &P)
+                    : launch(ensemble_kernel<DecompUmmaEvaluator<1>, 1>, grid, up.smem, st, "ensemble_decomp_umma_tf32", &P);
+        }
+      }
       if (use_rc(*desc)) {
         RcPlan plan;
         if (int rc = plan_rc(*desc, smem, rp, &plan)) return rc;
@@ -489,9 +575,9 @@ int bisip_ensemble_run(const bisip_model_desc* desc, int n_spectra, int n_walker
 #define BISIP_RC_LAUNCH(EVAL, NAME)                                                                       \
   return plan.two_per_sm ? launch_cluster(ensemble_kernel<EVAL, 2>, g, plan.cs, plan.smem, st, NAME, &P)  \
                          : launch_cluster(ensemble_kernel<EVAL, 1>, g, plan.cs, plan.smem, st, NAME, &P)
-        switch (desc->precision) {
-          case BISIP_PREC_TF32: BISIP_RC_LAUNCH(DecompTF32Evaluator<1>, "ensemble_decomp_tf32");
-          case BISIP_PREC_3XTF32: BISIP_RC_LAUNCH(DecompTF32Evaluator<3>, "ensemble_decomp_3xtf32");
+        switch (prec_planes(desc->precision)) {
+          case 1: BISIP_RC_LAUNCH(DecompTF32Evaluator<1>, "ensemble_decomp_tf32");
+          case 3: BISIP_RC_LAUNCH(DecompTF32Evaluator<3>, "ensemble_decomp_3xtf32");
           default: BISIP_RC_LAUNCH(DecompRCEvaluator, "ensemble_decomp_rc");
         }
 #undef BISIP_RC_LAUNCH

@@ -15,6 +15,7 @@
 #include "decomp_eval.cuh"
 #include "decomp_rc.cuh"
 #include "decomp_tf32.cuh"
+#include "decomp_umma.cuh"
 #include "models.cuh"
 
 namespace bisip {
@@ -281,6 +282,7 @@ struct DecompEvaluator {
   static constexpr bool kClustered = false;
   static constexpr bool kNeedsPrepare = false;
   __device__ __forceinline__ void prepare_row(int, const double*) {}
+  __device__ __forceinline__ void release() {}
   DecompSmem sm;
   DecompShape sh;
   int rows_pad;
@@ -305,6 +307,7 @@ struct DecompRCEvaluator {
   static constexpr bool kClustered = true;
   static constexpr bool kNeedsPrepare = false;
   __device__ __forceinline__ void prepare_row(int, const double*) {}
+  __device__ __forceinline__ void release() {}
   DecompRCSmem sm;
   DecompRCShape sh;
   int rows_pad;
@@ -331,6 +334,7 @@ struct DecompTF32Evaluator {
   static constexpr bool kClustered = true;
   static constexpr bool kNeedsPrepare = false;
   __device__ __forceinline__ void prepare_row(int, const double*) {}
+  __device__ __forceinline__ void release() {}
   DecompTF32Smem sm;
   DecompRCShape sh;
   int rows_pad;
@@ -349,6 +353,33 @@ struct DecompTF32Evaluator {
     side.finish();
     decomp_tf32_eval_chi<PREC>(sm, sh, prop, ndim, nrows, rows_pad, chi);
   }
+};
+
+// TF32 (PREC=1) / 3xTF32 (PREC=3) stage 2 on tcgen05 tensor cores: A (chargeability) and the FP32 accumulators
+// live in tensor memory, one M = 128 tile per half-step (<= 256 walkers, <= 64 frequencies).
+template <int PREC>
+struct DecompUmmaEvaluator {
+  static constexpr bool kClustered = false;
+  static constexpr bool kNeedsPrepare = false;
+  __device__ __forceinline__ void prepare_row(int, const double*) {}
+  DecompUmmaSmem sm;
+  DecompUmmaShape sh;
+  __device__ DecompUmmaEvaluator(const bisip_model_desc& d, int, int) : sh(d.n_freq, d.n_tau, d.n_coef) {}
+  static __host__ size_t smem_doubles(const bisip_model_desc& d, int) {
+    return decomp_umma_smem_doubles(DecompUmmaShape(d.n_freq, d.n_tau, d.n_coef), PREC);
+  }
+  __device__ double* carve(double* base, int) { return decomp_umma_carve<PREC>(sm, base, sh); }
+  __device__ void init(const bisip_model_desc& d, const double* w, const double* taus, const double* log_taus,
+                       const double* y, const double* yerr, double* red) {
+    decomp_umma_init<PREC>(sm, sh, d.c_exp, w, taus, log_taus, y, yerr, red);
+  }
+  __device__ double llconst() const { return sm.llconst; }
+  __device__ int iters_per_warp(int) const { return 0; }
+  __device__ void eval_chi(const double* prop, int ndim, int nrows, double* chi, RankSide& side) {
+    side.finish();
+    decomp_umma_eval<PREC, false>(sm, sh, prop, ndim, nrows, chi, nullptr);
+  }
+  __device__ void release() { decomp_umma_release(sm, sh); }   // frees the tensor memory
 };
 
 template <class Row>
@@ -372,6 +403,7 @@ struct VecEvaluator {
   __device__ __forceinline__ void prepare_row(int q, const double* th) {
     Row::prepare(th, n_modes, sm.rowc + (size_t)q * Row::kRC);
   }
+  __device__ __forceinline__ void release() {}
   __device__ void eval_chi(const double*, int, int nrows, double* chi, RankSide& side) {
     side.finish();
     vec_eval_chi<Row>(sm, N, n_modes, nrows, chi);
@@ -618,6 +650,7 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
     }
     if (P.flags && flag) atomicOr(P.flags + b, flag);
   }
+  ev.release();
   if (Eval::kClustered && cs > 1) cg::this_cluster().sync();   // peers may still read our shared memory
 }
 

@@ -52,8 +52,12 @@ enum bisip_model {
 
 enum bisip_precision {
   BISIP_PREC_FP64 = 0,  /* FP64 DMMA tensor tiles (decomposition) / FP64 pipe (others) */
-  BISIP_PREC_TF32 = 1,  /* decomposition stage 2 on TF32 tensor tiles, FP32 accumulate */
-  BISIP_PREC_3XTF32 = 2 /* error-compensated 3xTF32 split */
+  BISIP_PREC_TF32 = 1,  /* decomposition stage 2 on TF32 tensor cores, FP32 accumulate: tcgen05.mma with
+                           operands / accumulators in tensor memory when one 128-row tile holds a half-step
+                           (<= 256 walkers, n_freq <= 64, K planes fit in shared memory), mma.sync tiles otherwise */
+  BISIP_PREC_3XTF32 = 2,     /* error-compensated 3xTF32 split, same dispatch */
+  BISIP_PREC_TF32_MMA = 3,   /* TF32, always the mma.sync tile kernel (kept for the comparison study) */
+  BISIP_PREC_3XTF32_MMA = 4  /* 3xTF32, always the mma.sync tile kernel */
 };
 
 enum bisip_status {
