@@ -21,7 +21,9 @@ MAX_PCT = 16
 
 EXPORTS = ("bisip_abi_version", "bisip_last_error", "bisip_launch_count", "bisip_forward",
            "bisip_log_probability", "bisip_decomp_build_kernel", "bisip_n_keep",
-           "bisip_ensemble_run", "bisip_column_stats_workspace", "bisip_column_stats")
+           "bisip_ensemble_run", "bisip_column_stats_workspace", "bisip_column_stats",
+           "bisip_decomp_kernel_kind")
+KERNEL_KINDS = {0: "dmma", 1: "dmma-cluster", 2: "mma-tf32", 3: "tcgen05"}
 
 
 class BisipError(RuntimeError):
@@ -64,6 +66,8 @@ def load():
     lib.bisip_ensemble_run.argtypes = [C.POINTER(ModelDesc), i32, i32, i32, i32, C.c_uint64, C.c_uint32,
                                        dbl, i32, i32, vp, i64, vp, vp, i64, vp, vp, vp,
                                        vp, vp, vp, vp, vp, vp, vp]
+    lib.bisip_decomp_kernel_kind.restype = C.c_int
+    lib.bisip_decomp_kernel_kind.argtypes = [C.POINTER(ModelDesc), i32]
     lib.bisip_column_stats_workspace.restype = C.c_int64
     lib.bisip_column_stats_workspace.argtypes = [i32, i64, i32]
     lib.bisip_column_stats.restype = C.c_int

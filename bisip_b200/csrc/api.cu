@@ -465,6 +465,17 @@ int bisip_abi_version(void) { return BISIP_ABI_VERSION; }
 const char* bisip_last_error(void) { return g_err.c_str(); }
 int64_t bisip_launch_count(void) { return g_launches.load(); }
 
+int bisip_decomp_kernel_kind(const bisip_model_desc* desc, int n_walkers) {
+  if (int rc = check_desc(desc)) return rc;
+  if (desc->model != BISIP_MODEL_DECOMP || n_walkers < 2) return fail(BISIP_ERR_BAD_ARG, "bisip_decomp_kernel_kind: bad argument");
+  const size_t other = sampler_smem_bytes(n_walkers, desc->ndim);
+  if (plan_umma(*desc, other, (n_walkers + 1) / 2).ok) return BISIP_KERNEL_TCGEN05;
+  if (!use_rc(*desc)) return BISIP_KERNEL_DMMA;
+  RcPlan plan;
+  if (int rc = plan_rc(*desc, other, sampler_rows_pad(n_walkers), &plan)) return rc;
+  return desc->precision == BISIP_PREC_FP64 ? BISIP_KERNEL_DMMA_CLUSTER : BISIP_KERNEL_MMA_TF32;
+}
+
 int bisip_n_keep(int nsteps, int discard, int thin) {
   if (thin < 1 || discard < 0) return 0;
   const int first = discard + thin - 1;

@@ -23,6 +23,14 @@
 namespace bisip {
 
 static_assert(kThreads == 256, "decomp_umma.cuh maps 256 threads onto 128 TMEM lanes x 2 halves");
+#ifdef BISIP_PHASE_TIMING
+__device__ long long g_umma_ph[8];
+#define UMMA_T0 long long ut_ = clock64();
+#define UMMA_MARK(i) { if (blockIdx.x == 0 && threadIdx.x == 0) { long long n_ = clock64(); g_umma_ph[i] += n_ - ut_; ut_ = n_; } }
+#else
+#define UMMA_T0
+#define UMMA_MARK(i)
+#endif
 constexpr int kUmmaRows = 128;      // MMA M: proposals per tile (>= rows of a half-step: W <= 256)
 constexpr int kUmmaChunk = 64;      // taus per A buffer
 
@@ -44,7 +52,7 @@ struct DecompUmmaSmem {
   uint8_t* Bhi;       // [NC x SP] TF32, canonical K-major core matrices (8 columns x 16 bytes)
   uint8_t* Blo;       // PREC == 3
   double* Lk;         // [SP][8]   powers of log_tau per tau (zero padded)
-  double2* col;       // [NC]      (y/sigma, delta/sigma) per column
+  float4* col;        // [NC]      (y/sigma, delta/sigma) per column as two-float pairs {ys_hi, ys_lo, ds_hi, ds_lo}
   double* part;       // [128]     partial chi^2 of the imaginary half
   uint64_t* bar;      // [2] mbarriers the MMA completions arrive on (one per A buffer)
   uint32_t* tmem;     // tensor-memory base address
@@ -64,7 +72,7 @@ __device__ inline double* decomp_umma_carve(DecompUmmaSmem& s, double* base, con
   s.Bhi = p; p += sh.plane_bytes();
   s.Blo = p; if (PREC == 3) p += sh.plane_bytes();
   s.Lk = reinterpret_cast<double*>(p); p += (size_t)sh.SP * 64;
-  s.col = reinterpret_cast<double2*>(p); p += (size_t)sh.NC * 16;
+  s.col = reinterpret_cast<float4*>(p); p += (size_t)sh.NC * 16;
   s.part = reinterpret_cast<double*>(p); p += kUmmaRows * 8;
   s.bar = reinterpret_cast<uint64_t*>(p); p += 16;
   s.tmem = reinterpret_cast<uint32_t*>(p); p += 8;
@@ -93,6 +101,12 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tD, uint32_t tA, uint64_t 
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tD), "r"(tA), "l"(bdesc), "r"(idesc),
       "r"(accumulate)
       : "memory");
+}
+// one lane of a converged warp (warp-uniform call site): lets the compiler keep the MMA operands in uniform registers
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -152,7 +166,8 @@ __device__ inline void decomp_umma_init(DecompUmmaSmem& s, const DecompUmmaShape
       ds = part ? 0.0 : is;
       csum += 2.0 * log(e * e);
     }
-    s.col[n] = make_double2(ys, ds);
+    const float ysh = (float)ys, dsh = (float)ds;
+    s.col[n] = make_float4(ysh, (float)(ys - (double)ysh), dsh, (float)(ds - (double)dsh));
   }
   __syncthreads();
   double cs, sn;
@@ -195,55 +210,92 @@ __device__ inline void decomp_umma_release(DecompUmmaSmem& s, const DecompUmmaSh
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s.tbase), "r"(sh.tmem_cols()) : "memory");
 }
 
-// stage 1 of one 8-tau group for this thread's row -> hi / lo A planes in tensor memory
+__device__ __forceinline__ void lds_f64x2(uint32_t saddr, double& x, double& y) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(saddr));
+}
+__device__ __forceinline__ double lds_f64(uint32_t saddr) {
+  double x;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(saddr));
+  return x;
+}
+
+// Stage 1 for this thread's row over the 8-tau groups g = g0 + h, g0 + h + 2, ... < g1 of one A buffer:
+// M = sum_i a_i L[i][tau] in FP64 (ascending powers, like the reference), split into TF32 planes and stored to tensor
+// memory with one tcgen05.st per plane and group.  hi = round-to-nearest TF32 (magnitude + half ulp, masked — cvt.rna
+// without its inf/nan handling, |M| is O(1)); lo = the FP32 remainder truncated to TF32.  Lk is read with explicit
+// ld.shared (a pointer kept in a struct degrades to generic loads).
 template <int ND, int PREC>
-__device__ __forceinline__ void umma_stage1_group(const double* __restrict__ Lk8, const double (&a)[8], uint32_t ta_hi,
-                                                  uint32_t ta_lo) {
-  uint32_t hi[8], lo[8];
+__device__ __forceinline__ void umma_stage1_part(uint32_t lk_saddr, const double (&a)[8], uint32_t ta, int g0, int g1, int h) {
+  for (int g = g0 + h; g < g1; g += 2) {
+    const uint32_t la = lk_saddr + (uint32_t)g * 512u;
+    uint32_t hi[8], lo[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const double* L = Lk8 + e * 8;
-    double m = 0.0;
+    for (int e = 0; e < 8; ++e) {
+      double L[8];
 #pragma unroll
-    for (int i = 0; i < ND; ++i) m = fma(a[i], L[i], m);
-    split_tf32_umma(m, hi[e], lo[e]);
-  }
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(ta_hi), "r"(hi[0]), "r"(hi[1]),
-               "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7])
-               : "memory");
-  if (PREC == 3)
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(ta_lo), "r"(lo[0]), "r"(lo[1]),
-                 "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7])
+      for (int i = 0; i + 1 < ND; i += 2) lds_f64x2(la + e * 64 + i * 8, L[i], L[i + 1]);
+      if (ND & 1) L[ND - 1] = lds_f64(la + e * 64 + (ND - 1) * 8);
+      double m = 0.0;
+#pragma unroll
+      for (int i = 0; i < ND; ++i) m = fma(a[i], L[i], m);
+      const float xf = (float)m;
+      hi[e] = (__float_as_uint(xf) + 0x1000u) & 0xffffe000u;
+      lo[e] = (__float_as_uint(xf - __uint_as_float(hi[e])) + 0x1000u) & 0xffffe000u;
+    }
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(ta + 8 * g), "r"(hi[0]),
+                 "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7])
                  : "memory");
+    if (PREC == 3)
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(ta + 64 + 8 * g), "r"(lo[0]),
+                   "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7])
+                   : "memory");
+  }
 }
 
 template <int PREC>
-__device__ __forceinline__ void umma_stage1_dispatch(int ND, const double* Lk8, const double (&a)[8], uint32_t th, uint32_t tl) {
+__device__ __forceinline__ void umma_stage1_dispatch(int ND, uint32_t lk, const double (&a)[8], uint32_t ta, int g0, int g1, int h) {
   switch (ND) {
-    case 1: umma_stage1_group<1, PREC>(Lk8, a, th, tl); break;
-    case 2: umma_stage1_group<2, PREC>(Lk8, a, th, tl); break;
-    case 3: umma_stage1_group<3, PREC>(Lk8, a, th, tl); break;
-    case 4: umma_stage1_group<4, PREC>(Lk8, a, th, tl); break;
-    case 5: umma_stage1_group<5, PREC>(Lk8, a, th, tl); break;
-    case 6: umma_stage1_group<6, PREC>(Lk8, a, th, tl); break;
-    case 7: umma_stage1_group<7, PREC>(Lk8, a, th, tl); break;
-    default: umma_stage1_group<8, PREC>(Lk8, a, th, tl); break;
+    case 1: umma_stage1_part<1, PREC>(lk, a, ta, g0, g1, h); break;
+    case 2: umma_stage1_part<2, PREC>(lk, a, ta, g0, g1, h); break;
+    case 3: umma_stage1_part<3, PREC>(lk, a, ta, g0, g1, h); break;
+    case 4: umma_stage1_part<4, PREC>(lk, a, ta, g0, g1, h); break;
+    case 5: umma_stage1_part<5, PREC>(lk, a, ta, g0, g1, h); break;
+    case 6: umma_stage1_part<6, PREC>(lk, a, ta, g0, g1, h); break;
+    case 7: umma_stage1_part<7, PREC>(lk, a, ta, g0, g1, h); break;
+    default: umma_stage1_part<8, PREC>(lk, a, ta, g0, g1, h); break;
   }
+}
+
+// One elected thread: the MMAs of K steps [j0, j1) of one A buffer.  Descriptors advance by 256 bytes (16 units) per
+// K step, A by 8 tensor-memory columns.  Small terms first: A_lo B_hi, A_hi B_lo, then A_hi B_hi.
+template <int PREC>
+__device__ __forceinline__ void umma_issue(uint32_t tD, uint32_t tA, uint64_t dhi, uint64_t dlo, uint32_t idesc, int j0, int j1,
+                                           bool overwrite) {
+  uint32_t acc = overwrite ? 0u : 1u;
+  if (PREC == 3) {
+    for (int j = j0; j < j1; ++j) { umma_tf32_ts(tD, tA + 64 + 8 * j, dhi + 16u * j, idesc, acc); acc = 1u; }
+    for (int j = j0; j < j1; ++j) umma_tf32_ts(tD, tA + 8 * j, dlo + 16u * j, idesc, 1u);
+  }
+  for (int j = j0; j < j1; ++j) { umma_tf32_ts(tD, tA + 8 * j, dhi + 16u * j, idesc, acc); acc = 1u; }
 }
 
 // Evaluate nrows <= 128 proposals.  WANT_Z = false: chi[q] = sum_c ((y_c - Z_c)/sigma_c)^2 (caller barriers
 // before reading); WANT_Z = true: Zout[q][2][N] (forward only; init was called with y == nullptr).
 // 256 threads: thread = (row r = tid & 127, half h = tid >> 7); h splits the tau groups in stage 1 and the
 // real | imaginary columns in the epilogue.  Warp w may touch TMEM lanes [32 (w & 3), +32) only — exactly its rows.
+// Each A buffer is produced in two parts so that the MMAs of the first part run under stage 1 of the second.
 template <int PREC, bool WANT_Z>
 __device__ inline void decomp_umma_eval(DecompUmmaSmem& s, const DecompUmmaShape& sh, const double* __restrict__ prop,
                                         int ndim, int nrows, double* __restrict__ chi, double* __restrict__ Zout) {
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int r = tid & (kUmmaRows - 1), h = tid >> 7;
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);               // warp-uniform by construction
+  const int r = tid & (kUmmaRows - 1), h = warp >> 2;
   const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
   const bool warp_live = 32 * (warp & 3) < nrows;
-  const uint32_t tD = s.tbase, tA0 = s.tbase + 128;
+  const uint32_t tbase = __shfl_sync(0xffffffffu, s.tbase, 0);
+  const uint32_t tD = tbase, tA0 = tbase + 128;
   const uint32_t baddr = smem_u32(s.bar);
+  const uint32_t lk_saddr = smem_u32(s.Lk);
   double R0 = 0.0;
   double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   if (r < nrows) {
@@ -253,28 +305,51 @@ __device__ inline void decomp_umma_eval(DecompUmmaSmem& s, const DecompUmmaShape
     for (int i = 0; i < 8; ++i) a[i] = (i < sh.D) ? R0 * q[1 + i] : 0.0;
   }
   const uint32_t idesc = umma_idesc(sh.NC);
+  UMMA_T0
   for (int c = 0; c < sh.nchunks; ++c) {
     const int k0 = c * kUmmaChunk, kt = min(kUmmaChunk, sh.SP - k0);      // taus of this chunk (multiple of 8)
+    const int ng = kt >> 3, gsplit = min(ng, ((ng + 3) >> 2) << 1);
     const uint32_t tA = tA0 + (uint32_t)(c & 1) * 128;                    // hi at tA, lo at tA + 64
+    const uint64_t dhi = umma_b_desc(smem_u32(s.Bhi) + 32 * k0, sh.SP);   // 32 bytes per tau: 256 per K step
+    const uint64_t dlo = umma_b_desc(smem_u32(s.Blo) + 32 * k0, sh.SP);
     if (warp_live) {
-      for (int g = h; g < (kt >> 3); g += 2)
-        umma_stage1_dispatch<PREC>(sh.D, s.Lk + (size_t)(k0 + 8 * g) * 8, a, tA + lane_base + 8 * g, tA + 64 + lane_base + 8 * g);
+      umma_stage1_dispatch<PREC>(sh.D, lk_saddr + (uint32_t)k0 * 64u, a, tA + lane_base, 0, gsplit, h);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
+    UMMA_MARK(0)
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    UMMA_MARK(1)
+    if (warp == 0) {
       tc_fence_after();
-      const uint32_t bhi = smem_u32(s.Bhi) + 32 * k0, blo = smem_u32(s.Blo) + 32 * k0;   // 256 bytes per K step of 8 taus
-      const int ks = kt >> 3;
-      uint32_t acc = c > 0 ? 1u : 0u;
-      if (PREC == 3) {
-        for (int j = 0; j < ks; ++j) { umma_tf32_ts(tD, tA + 64 + 8 * j, umma_b_desc(bhi + 256 * j, sh.SP), idesc, acc); acc = 1u; }
-        for (int j = 0; j < ks; ++j) umma_tf32_ts(tD, tA + 8 * j, umma_b_desc(blo + 256 * j, sh.SP), idesc, 1u);
+      if (elect_one()) {
+        umma_issue<PREC>(tD, tA, dhi, dlo, idesc, 0, gsplit, c == 0);
+        if (gsplit == ng)
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(baddr + 8 * (c & 1))
+                       : "memory");
       }
-      for (int j = 0; j < ks; ++j) { umma_tf32_ts(tD, tA + 8 * j, umma_b_desc(bhi + 256 * j, sh.SP), idesc, acc); acc = 1u; }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(baddr + 8 * (c & 1))
-                   : "memory");
+      __syncwarp();
+    }
+    UMMA_MARK(2)
+    if (gsplit < ng) {
+      if (warp_live) {
+        umma_stage1_dispatch<PREC>(sh.D, lk_saddr + (uint32_t)k0 * 64u, a, tA + lane_base, gsplit, ng, h);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
+      UMMA_MARK(0)
+      tc_fence_before();
+      __syncthreads();
+      UMMA_MARK(1)
+      if (warp == 0) {
+        tc_fence_after();
+        if (elect_one()) {
+          umma_issue<PREC>(tD, tA, dhi, dlo, idesc, gsplit, ng, false);
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(baddr + 8 * (c & 1))
+                       : "memory");
+        }
+        __syncwarp();
+      }
+      UMMA_MARK(2)
     }
     // Double-buffered A: chunk c+1 is written while chunk c is multiplied, chunk c+2 re-uses the buffer of chunk c —
     // so chunk c-1 is awaited here (one chunk behind) and the last chunk below.  One mbarrier per buffer: between
@@ -291,10 +366,15 @@ __device__ inline void decomp_umma_eval(DecompUmmaSmem& s, const DecompUmmaShape
     s.phase ^= 1u << bi;
   }
   tc_fence_after();
+  UMMA_MARK(3)
   // ---- epilogue: D row r, columns [h NCH, (h+1) NCH) ---------------------------------------------------------
+  // The accumulators are FP32, so the residual is formed in FP32 too: c = y/s - R0 d/s is evaluated with two-float
+  // operands (head FMA + tail corrections), which keeps its error below the accumulator's own rounding.
   double acc = 0.0;
   if (warp_live) {
     const uint32_t td = tD + lane_base + (uint32_t)(h * sh.NCH);
+    const float R0h = (float)R0, R0l = (float)(R0 - (double)R0h);
+    float ch[4] = {0.f, 0.f, 0.f, 0.f};
     for (int c0 = 0; c0 < sh.NCH; c0 += 16) {
       uint32_t v[16];
       asm volatile(
@@ -313,22 +393,34 @@ __device__ inline void decomp_umma_eval(DecompUmmaSmem& s, const DecompUmmaShape
           }
         }
       } else {
-        const double2* col = s.col + h * sh.NCH + c0;
+        const uint32_t ca = smem_u32(s.col) + (uint32_t)(h * sh.NCH + c0) * 16u;
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-          const double2 yd = col[e];
-          const double res = fma(-R0, yd.y, yd.x) + (double)__uint_as_float(v[e]);
-          acc = fma(res, res, acc);
+          float ysh, ysl, dsh, dsl;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ysh), "=f"(ysl), "=f"(dsh), "=f"(dsl) : "r"(ca + e * 16));
+          const float d = __uint_as_float(v[e]);
+          float res;
+          if (h == 0) {
+            const float t = fmaf(-R0h, dsh, ysh) + d;
+            const float corr = fmaf(-R0l, dsh, fmaf(-R0h, dsl, ysl));
+            res = t + corr;
+          } else {
+            res = (ysh + d) + ysl;
+          }
+          ch[e & 3] = fmaf(res, res, ch[e & 3]);
         }
       }
     }
+    acc = ((double)ch[0] + (double)ch[1]) + ((double)ch[2] + (double)ch[3]);
   }
   tc_fence_before();
+  UMMA_MARK(4)
   if (!WANT_Z) {
     if (h == 1) s.part[r] = acc;
     __syncthreads();
     if (h == 0 && r < nrows) chi[r] = acc + s.part[r];
   }
+  UMMA_MARK(5)
 }
 
 }  // namespace bisip

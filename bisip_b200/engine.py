@@ -49,6 +49,17 @@ def _chk_cuda_f64(*tensors):
             raise _lib.BisipError("engine tensors must be contiguous CUDA float64")
 
 
+def decomp_kernel_kind(spec, n_freq, n_walkers):
+    """Name of the decomposition kernel ``ensemble_run`` will launch for this model spec and walker count:
+    'dmma', 'dmma-cluster', 'mma-tf32' or 'tcgen05' (needs a CUDA device: the answer depends on its shared memory)."""
+    lib = _lib.load()
+    d = spec.desc(n_freq)
+    rc = lib.bisip_decomp_kernel_kind(C.byref(d), int(n_walkers))
+    if rc < 0:
+        _lib.check(rc, "bisip_decomp_kernel_kind")
+    return _lib.KERNEL_KINDS[rc]
+
+
 def forward(spec, theta, w):
     """theta (B, n, ndim), w (N,) or (B, N)  ->  Z (B, n, 2, N).  Reference: Model.forward."""
     lib = _lib.load()

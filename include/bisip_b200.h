@@ -86,6 +86,16 @@ const char *bisip_last_error(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t bisip_launch_count(void);
 
+/* Which decomposition kernel bisip_ensemble_run will launch for (desc, n_walkers): every one of them is a CUDA
+ * kernel of this library (there is no CPU path); the choice depends on precision, tau-grid size and walker count. */
+enum bisip_kernel_kind {
+  BISIP_KERNEL_DMMA = 0,         /* FP64 mma.sync (DMMA) tiles, n_tau <= 64 */
+  BISIP_KERNEL_DMMA_CLUSTER = 1, /* FP64 DMMA, stage-1 recompute, columns split over a CTA cluster (n_tau > 64) */
+  BISIP_KERNEL_MMA_TF32 = 2,     /* TF32 / 3xTF32 mma.sync tiles */
+  BISIP_KERNEL_TCGEN05 = 3       /* TF32 / 3xTF32 tcgen05.mma, operands and accumulators in tensor memory */
+};
+int bisip_decomp_kernel_kind(const bisip_model_desc *desc, int n_walkers);
+
 /* Forward model for n_spectra x n_theta parameter vectors.  Z as documented above. */
 int bisip_forward(const bisip_model_desc *desc, int n_spectra, int n_theta,
                   const double *theta, const double *w, int64_t w_stride,

@@ -129,9 +129,11 @@ def test_decomp_kernel_matrix(gold_fl, gold_ld):
 
 
 @pytest.mark.parametrize("tag", ['syn_decomp_s64', 'syn_decomp_s128', 'syn_decomp_s256'])
-@pytest.mark.parametrize("prec,ztol,lptol", [('tf32', 1e-3, 3e-3), ('3xtf32', 2e-5, 5e-5)])
+@pytest.mark.parametrize("prec,ztol,lptol", [('tf32', 1e-3, 3e-3), ('3xtf32', 2e-5, 5e-5),
+                                             ('tf32-mma', 1e-3, 3e-3), ('3xtf32-mma', 2e-5, 5e-5)])
 def test_reduced_precision_within_stated_tolerance(tag, prec, ztol, lptol, gold_fl):
-    """TF32 / 3xTF32 stage 2 (FP64 stage 1, FP32 accumulate) against the reference golden values.
+    """TF32 / 3xTF32 stage 2 (FP64 stage 1, FP32 accumulate) against the reference golden values, on the tcgen05
+    kernel ('tf32', '3xtf32' where the problem fits one tile) and on the mma.sync tiles ('*-mma', and the fallback).
     Stated tolerances (measured in profiles/r01_tf32_study.md, with head-room):
       forward  max|dZ|/max|Z| <= 1e-3 (tf32), 2e-5 (3xtf32);  log-prob relative <= 3e-3 / 5e-5."""
     from bisip_b200 import _lib, engine, synthetic
@@ -166,3 +168,58 @@ def test_3xtf32_sampler_runs_and_agrees_statistically(gold_fl):
     shift = np.abs(out['3xtf32']['percentiles'][:, 1] - out['fp64']['percentiles'][:, 1]) / out['fp64']['std']
     assert shift.max() < 0.5             # medians agree within Monte-Carlo error
     assert np.abs(out['3xtf32']['acceptance_fraction'] - out['fp64']['acceptance_fraction']).max() < 0.03
+
+
+TCGEN05_SHAPES = [  # (n_freq, n_tau, poly_deg, walkers, c_exp, precision, expected kernel)
+    (64, 64, 4, 256, 1.0, '3xtf32', 'tcgen05'),      # C5 shape: one M=128 tile per half-step, two CTAs per SM
+    (64, 64, 4, 256, 1.0, 'tf32', 'tcgen05'),
+    (20, 40, 4, 32, 1.0, '3xtf32', 'tcgen05'),       # bundled-file shape (C1): 16-row half-steps, padded columns / taus
+    (33, 50, 3, 66, 0.5, '3xtf32', 'tcgen05'),       # odd everything, Warburg
+    (64, 8, 0, 14, 1.0, '3xtf32', 'tcgen05'),        # a single K step, poly_deg 0
+    (64, 64, 7, 254, 1.0, '3xtf32', 'tcgen05'),      # poly_deg 7 (8 coefficients), 127-row half-steps
+    (64, 128, 4, 256, 1.0, '3xtf32', 'tcgen05'),     # two 64-tau chunks: double-buffered A, one CTA per SM
+    (64, 256, 4, 128, 1.0, 'tf32', 'tcgen05'),       # four chunks (C4 tau grid)
+    (64, 256, 4, 128, 1.0, '3xtf32', 'mma-tf32'),    # K planes exceed shared memory -> mma.sync tiles
+    (64, 64, 4, 258, 1.0, '3xtf32', 'mma-tf32'),     # 129-row half-steps do not fit the 128-lane tile
+    (96, 64, 4, 64, 1.0, '3xtf32', 'mma-tf32'),      # 192 columns > 128
+    (64, 64, 4, 256, 1.0, '3xtf32-mma', 'mma-tf32'),
+    (64, 64, 4, 256, 1.0, 'fp64', 'dmma'),
+    (64, 128, 4, 256, 1.0, 'fp64', 'dmma-cluster'),
+]
+
+
+@pytest.mark.parametrize("N,S,P,W,c_exp,prec,kind", TCGEN05_SHAPES)
+def test_tcgen05_dispatch_and_agreement(N, S, P, W, c_exp, prec, kind):
+    """Every shape class of the tcgen05 decomposition kernel (and each documented fallback): the library reports
+    the kernel it will launch, its log-probability agrees with the FP64 DMMA path within the stated TF32 / 3xTF32
+    tolerance, and a short sampler run from the same p0 / seed produces no NaN flag and the same acceptance."""
+    from bisip_b200 import _lib, engine, synthetic
+    from bisip_b200.batch import BatchInversion
+    dev = _lib.require_cuda()
+    _, w = synthetic.frequencies(N)
+    kw = dict(poly_deg=P, n_tau=S, c_exp=c_exp)
+    probe = BatchInversion('decomp', w, np.zeros((1, 2, N)), np.ones((1, 2, N)), device=dev, **kw)
+    fwd = lambda th, ww: engine.forward(probe._spec(), _lib.dev_f64(th[:, None, :], dev), _lib.dev_f64(ww, dev))[:, 0].cpu().numpy()
+    B = 5
+    syn = synthetic.make('decomp', 0, B, fwd, N=N, poly_deg=P, n_tau=S)
+    inv = {p: BatchInversion('decomp', w, syn['zn'], syn['zn_err'], nwalkers=W, nsteps=60, seed=11, device=dev, precision=p, **kw)
+           for p in ('fp64', prec)}
+    assert engine.decomp_kernel_kind(inv[prec]._spec(), N, W) == kind
+    truth = syn['theta_true'].copy()
+    truth[:, 0] /= syn['norm_factor']
+    rng = np.random.default_rng(5)
+    th = truth[:, None, :] * (1 + 2e-3 * rng.standard_normal((B, 333, P + 2)))
+    th[:, -1, 0] = 2.0                                                      # one row outside the prior box
+    args = (_lib.dev_f64(th, dev), _lib.dev_f64(w, dev), _lib.dev_f64(syn['zn'], dev), _lib.dev_f64(syn['zn_err'], dev),
+            _lib.dev_f64(inv['fp64'].param_bounds, dev))
+    lp = {p: engine.log_probability(inv[p]._spec(), *args).cpu().numpy() for p in inv}
+    assert np.all(np.isneginf(lp[prec][:, -1])) and np.all(np.isfinite(lp[prec][:, :-1]))
+    tol = 0.0 if prec == 'fp64' else (3e-3 if prec.startswith('tf32') else 5e-5)
+    assert lp_err(lp[prec][:, :-1], lp['fp64'][:, :-1]).max() <= tol
+    Z = {p: engine.forward(inv[p]._spec(), args[0], args[1]).cpu().numpy() for p in inv}
+    ztol = 0.0 if prec == 'fp64' else (1e-3 if prec.startswith('tf32') else 2e-5)
+    assert max(normwise(Z[prec][b], Z['fp64'][b]).max() for b in range(B)) <= ztol
+    p0 = inv['fp64'].draw_p0(0, B)
+    res = {p: inv[p].fit(p0=p0.copy(), discard=30, thin=1) for p in inv}
+    assert np.all(res[prec]['flags'] == 0)
+    assert np.abs(res[prec]['acceptance_fraction'] - res['fp64']['acceptance_fraction']).max() < 0.1
