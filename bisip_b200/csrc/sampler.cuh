@@ -640,12 +640,6 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
     PHASE_MARK(4)
   }
   PHASE_PRINT
-#ifdef BISIP_PHASE_TIMING
-  if (blockIdx.x == 0 && threadIdx.x == 0 && g_umma_ph[0])
-    printf("umma eval cycles/step: stage1 %.0f  barrier %.0f  issue %.0f  mma-wait %.0f  epilogue %.0f  tail %.0f\n",
-           (double)g_umma_ph[0] / P.nsteps, (double)g_umma_ph[1] / P.nsteps, (double)g_umma_ph[2] / P.nsteps,
-           (double)g_umma_ph[3] / P.nsteps, (double)g_umma_ph[4] / P.nsteps, (double)g_umma_ph[5] / P.nsteps);
-#endif
   // ---- final state ------------------------------------------------------------------------------
   if (writer) {
     double* gco = P.coords + (size_t)b * W * ndim;
