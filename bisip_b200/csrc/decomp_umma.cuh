@@ -66,7 +66,7 @@ struct DecompUmmaShape {
 //   R    [8][8] doubles:  L_i = sum_{j<=i} R[i][j] q_j
 //   col  [NC] float4 {c0_hi, c0_lo, delta/sigma, -}: c0 = (y - kUmmaR0c delta)/sigma as a two-float pair
 //   part [128] doubles: partial chi^2 of the imaginary half
-//   bar  [2] mbarriers (stage-1 MMAs, stage-2 MMAs);  tmem: tensor-memory base address written by tcgen05.alloc
+//   bar  [5] mbarriers (stage-1 MMAs, column blocks of the stage-2 MMAs; 3 in use);  tmem: base address from tcgen05.alloc
 struct DecompUmmaSmem {
   uint8_t* p0;        // 128-byte aligned start (= Bhi)
   double llconst;
@@ -88,7 +88,7 @@ struct DecompUmmaOff {
     o.col = o.R + 512u;
     o.part = o.col + (uint32_t)sh.NC * 16u;
     o.bar = o.part + kUmmaRows * 8u;
-    o.tmem = o.bar + 16u;
+    o.tmem = o.bar + 40u;
     return o;
   }
 };
@@ -96,7 +96,7 @@ struct DecompUmmaOff {
 __host__ __device__ inline size_t decomp_umma_smem_doubles(const DecompUmmaShape& sh, int prec) {
   const size_t planes = prec == 3 ? 2 : 1;
   return 16 + planes * sh.plane_bytes() / 8 + 3 * sh.qplane_bytes() / 8 + (size_t)sh.SQ * 8 + 64 + 2 * (size_t)sh.NC +
-         kUmmaRows + 4;
+         kUmmaRows + 8;
 }
 
 template <int PREC>
@@ -216,8 +216,7 @@ __device__ inline void decomp_umma_init(DecompUmmaSmem& s, const DecompUmmaShape
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 32) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(l.bar)) : "memory");
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(l.bar + 1)) : "memory");
+    for (int i = 0; i < 5; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(l.bar + i)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   {
@@ -394,14 +393,19 @@ __device__ inline void decomp_umma_eval(DecompUmmaSmem& s, const DecompUmmaShape
   tc_fence_before();
   __syncthreads();
   UMMA_MARK(0)
-  const uint32_t idesc2 = umma_idesc(sh.NC);
+  // stage-2 column blocks: the real and the imaginary columns (N = NCH each).  Measured on B200 (C5 shape, 3xTF32):
+  // one N = 128 block 5.36e9 evals/s, two blocks 6.00e9, four N = 32 blocks 5.11e9 (short instructions pay a fixed cost).
+  const int nblk = 2, bw = sh.NCH;
+  const uint32_t idescb = umma_idesc(bw);
   const uint32_t q0a = sb + o.Q, qpb = (uint32_t)sh.qplane_bytes();
   for (int c = 0; c < sh.nchunks; ++c) {
     const int k0 = c * kUmmaChunk, kt = min(kUmmaChunk, sh.SP - k0);      // taus of this chunk (multiple of 8)
     const int nq = min(kUmmaChunk, sh.SQ - k0);                           // stage-1 N (multiple of 16)
     const int ng = kt >> 3;
-    // ---- stage 1: M = b Q (six plane products, smallest first) -> tM -----------------------------------------------
-    if (warp == 0) {
+    // ---- stage 1: M = b Q (six plane products, smallest first) -> tM.  Issued by the same lane as stage 2:
+    //      tcgen05.commit only tracks the issuing thread's MMAs, and the wait below must also cover stage 2 of
+    //      the previous chunk before its A planes are overwritten ------------------------------------------------------
+    if (warp == 7) {
       tc_fence_after();
       if (elect_one()) {
         const uint32_t id1 = umma_idesc(nq);
@@ -443,56 +447,66 @@ __device__ inline void decomp_umma_eval(DecompUmmaSmem& s, const DecompUmmaShape
     tc_fence_before();
     __syncthreads();
     UMMA_MARK(2)
-    // ---- stage 2: D (+)= M (K/sigma); 256 bytes of each plane per K step of 8 taus ----------------------------------
-    if (warp == 0) {
+    // ---- stage 2: D (+)= M (K/sigma); 256 bytes of each plane per K step of 8 taus.  The columns are issued as two
+    //      blocks (real, imaginary), each committed to its own mbarrier, so the epilogue of the real block (half 0)
+    //      runs under the MMAs of the imaginary one.  Warp 7 issues: it belongs to the half whose block finishes last.
+    if (warp == 7) {
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t dhi = umma_desc(sb + 32 * k0, 32 * sh.SP), dlo = umma_desc(sb + o.Blo + 32 * k0, 32 * sh.SP);
-        uint32_t acc = c > 0 ? 1u : 0u;
-        if (PREC == 3) {
-          for (int j = 0; j < ng; ++j) { umma_tf32_ts(tD, tA + 64 + 8 * j, dhi + 16u * j, idesc2, acc); acc = 1u; }
-          for (int j = 0; j < ng; ++j) umma_tf32_ts(tD, tA + 8 * j, dlo + 16u * j, idesc2, 1u);
+        for (int blk = 0; blk < nblk; ++blk) {
+          const int n0 = (blk & 1) * sh.NCH + (blk >> 1) * bw;           // first column of the block
+          const uint32_t boff = (uint32_t)(n0 >> 3) * (uint32_t)(32 * sh.SP) + 32u * k0;
+          const uint64_t dhi = umma_desc(sb + boff, 32 * sh.SP), dlo = umma_desc(sb + o.Blo + boff, 32 * sh.SP);
+          uint32_t acc = c > 0 ? 1u : 0u;
+          if (PREC == 3) {
+            for (int j = 0; j < ng; ++j) { umma_tf32_ts(tD + n0, tA + 64 + 8 * j, dhi + 16u * j, idescb, acc); acc = 1u; }
+            for (int j = 0; j < ng; ++j) umma_tf32_ts(tD + n0, tA + 8 * j, dlo + 16u * j, idescb, 1u);
+          }
+          for (int j = 0; j < ng; ++j) { umma_tf32_ts(tD + n0, tA + 8 * j, dhi + 16u * j, idescb, acc); acc = 1u; }
+          if (c + 1 == sh.nchunks) umma_commit(barD + 8 * blk);
         }
-        for (int j = 0; j < ng; ++j) { umma_tf32_ts(tD, tA + 8 * j, dhi + 16u * j, idesc2, acc); acc = 1u; }
-        if (c + 1 == sh.nchunks) umma_commit(barD);
       }
       __syncwarp();
     }
   }
-  mbar_wait(barD, (s.phase >> 1) & 1u);
-  s.phase ^= 2u;
-  tc_fence_after();
   UMMA_MARK(3)
-  // ---- epilogue: D row r, columns [h NCH, (h+1) NCH) ---------------------------------------------------------
+  // ---- epilogue: D row r; half h owns column block h (columns [h NCH, (h+1) NCH)) --------------------------------
   // The accumulators are FP32, so the residual is formed in FP32 too: res = c0 - dR0 * delta/sigma + D with c0 a
   // two-float constant per column (see kUmmaR0c), which keeps its error below the accumulators' own rounding.
   double acc = 0.0;
-  if (warp_live) {
-    const uint32_t td = tD + lane_base + (uint32_t)(h * sh.NCH);
+  {
     const float dR0 = (float)(R0 - kUmmaR0c);
     float ch[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int c0 = 0; c0 < sh.NCH; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld16(td + c0, v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (WANT_Z) {
-        if (r < nrows) {
+    for (int i = 0; i < nblk / 2; ++i) {
+      const int blk = h + 2 * i;
+      mbar_wait(barD + 8 * blk, (s.phase >> (1 + blk)) & 1u);
+      s.phase ^= 2u << blk;
+      tc_fence_after();
+      if (!warp_live) continue;
+      const uint32_t td = tD + lane_base + (uint32_t)(h * sh.NCH + i * bw);
+      for (int c0 = 0; c0 < bw; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(td + c0, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (WANT_Z) {
+          if (r < nrows) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const int j = i * bw + c0 + e;
+              if (j < sh.N) Zout[(size_t)r * 2 * sh.N + h * sh.N + j] = (h ? 0.0 : R0) - (double)__uint_as_float(v[e]);
+            }
+          }
+        } else {
+          const uint32_t ca = sb + o.col + (uint32_t)(h * sh.NCH + i * bw + c0) * 16u;
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            const int j = c0 + e;
-            if (j < sh.N) Zout[(size_t)r * 2 * sh.N + h * sh.N + j] = (h ? 0.0 : R0) - (double)__uint_as_float(v[e]);
+            float c0h, c0l, dsg, unused;
+            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c0h), "=f"(c0l), "=f"(dsg), "=f"(unused) : "r"(ca + e * 16));
+            const float d = __uint_as_float(v[e]);
+            const float head = h == 0 ? fmaf(-dR0, dsg, c0h) : c0h;          // imaginary columns: delta = 0
+            const float res = (head + d) + c0l;
+            ch[e & 3] = fmaf(res, res, ch[e & 3]);
           }
-        }
-      } else {
-        const uint32_t ca = sb + o.col + (uint32_t)(h * sh.NCH + c0) * 16u;
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          float c0h, c0l, dsg, unused;
-          asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c0h), "=f"(c0l), "=f"(dsg), "=f"(unused) : "r"(ca + e * 16));
-          const float d = __uint_as_float(v[e]);
-          const float head = h == 0 ? fmaf(-dR0, dsg, c0h) : c0h;          // imaginary columns: delta = 0
-          const float res = (head + d) + c0l;
-          ch[e & 3] = fmaf(res, res, ch[e & 3]);
         }
       }
     }

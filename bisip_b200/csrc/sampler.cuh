@@ -73,6 +73,8 @@ struct SamplerSmem {
   int* acc;        // [W]
   int* inb;        // [rows_pad]
   int* partner;    // [rows_pad]     index into the complementary half
+  int* hist;       // [260]          bucket counters / starts of the key ranking (16-byte aligned)
+  uint32_t* sorted;// [Wpad4]        keys grouped by bucket
 };
 
 __host__ __device__ inline int sampler_rows_pad(int W) { return ceil_div((W + 1) / 2, 16) * 16; }
@@ -80,8 +82,8 @@ __host__ __device__ inline int sampler_rows_pad(int W) { return ceil_div((W + 1)
 __host__ __device__ inline size_t sampler_smem_bytes(int W, int ndim) {
   const int rp = sampler_rows_pad(W);
   size_t dbl = (size_t)W * ndim + W + (size_t)rp * ndim + rp + 2 * rp + rp + rp + 4 * ndim + kWarps;
-  size_t words = (size_t)(W + 4) + 2 * W + W + rp + rp;
-  return dbl * 8 + words * 4 + 32;
+  size_t words = (size_t)(W + 4) + 2 * W + W + rp + rp + 260 + (W + 4);
+  return dbl * 8 + words * 4 + 48;
 }
 
 __device__ inline void sampler_carve(SamplerSmem& s, double* base, int W, int ndim) {
@@ -101,6 +103,8 @@ __device__ inline void sampler_carve(SamplerSmem& s, double* base, int W, int nd
   s.acc = s.list + 2 * W;
   s.inb = s.acc + W;
   s.partner = s.inb + rp;
+  s.hist = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(s.partner + rp) + 15) & ~uintptr_t(15));
+  s.sorted = reinterpret_cast<uint32_t*>(s.hist + 260);
 }
 
 // strict box prior, models.py:64-69 (NaN -> outside)
@@ -275,6 +279,56 @@ struct RankSide {
     on = false;
   }
 };
+
+// Ranking of the shuffle keys in O(W): walkers are binned by the top 8 bits of their (uniform random) key, the 256
+// bin counts are scanned by one warp, and each walker then only compares itself with the keys of its own bin (one
+// on average).  rank = bin start + smaller keys in the bin — the same number the all-pairs count above produces, so
+// chains stay bit-identical; the shared-memory atomics only decide where a key is parked inside its bin.
+// All threads of the CTA; W <= NT.  Ends without a barrier (the caller synchronises before list_out is read).
+template <int NT>
+__device__ __forceinline__ void rank_keys_binned(const uint32_t* __restrict__ keys, int* __restrict__ list_out, int W,
+                                                 int* __restrict__ hist, uint32_t* __restrict__ sorted) {
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 256; i += NT) hist[i] = 0;
+  __syncthreads();
+  uint32_t key = 0;
+  int bin = 0, slot = 0;
+  if (tid < W) {
+    key = keys[tid];
+    bin = (int)(key >> 24);
+    slot = atomicAdd(&hist[bin], 1);
+  }
+  __syncthreads();
+  if (tid < 32) {                                  // exclusive scan of the 256 counters, 8 per lane
+    int4* h4 = reinterpret_cast<int4*>(hist);
+    const int4 a = h4[2 * tid], c = h4[2 * tid + 1];
+    const int s0 = a.x, s1 = s0 + a.y, s2 = s1 + a.z, s3 = s2 + a.w, s4 = s3 + c.x, s5 = s4 + c.y, s6 = s5 + c.z;
+    const int tot = s6 + c.w;
+    int inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, inc, o);
+      if (tid >= o) inc += n;
+    }
+    const int base = inc - tot;
+    h4[2 * tid] = make_int4(base, base + s0, base + s1, base + s2);
+    h4[2 * tid + 1] = make_int4(base + s3, base + s4, base + s5, base + s6);
+    if (tid == 31) hist[256] = inc;
+  }
+  __syncthreads();
+  int start = 0;
+  if (tid < W) {
+    start = hist[bin];
+    sorted[start + slot] = key;
+  }
+  __syncthreads();
+  if (tid < W) {
+    const int end = hist[bin + 1];
+    int cnt = 0;
+    for (int j = start; j < end; ++j) cnt += sorted[j] < key ? 1 : 0;
+    list_out[start + cnt] = tid;
+  }
+}
 
 // Evaluator adaptors -------------------------------------------------------------------
 template <int KC>
@@ -536,8 +590,12 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
   // prologue: split of step 0 and the draws of its first half-step
   gen_keys((uint32_t)P.step0, tid, NT);
   __syncthreads();
-  side.begin(s.keys, s.list, W, 0);
-  side.finish();
+  if (W <= NT) {
+    rank_keys_binned<NT>(s.keys, s.list, W, s.hist, s.sorted);
+  } else {
+    side.begin(s.keys, s.list, W, 0);
+    side.finish();
+  }
   gen_proposal_draws((uint32_t)P.step0, 0, tid, NT);
   __syncthreads();
 
@@ -619,8 +677,12 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
       PHASE_MARK(3)
     }
     // ---- split of the next step: rank its keys (drawn during this step's first accept phase) ---------
-    side.begin(s.keys, list_next, W, 0);
-    side.finish();
+    if (W <= NT) {
+      rank_keys_binned<NT>(s.keys, list_next, W, s.hist, s.sorted);
+    } else {
+      side.begin(s.keys, list_next, W, 0);
+      side.finish();
+    }
     PHASE_MARK(0)
     // ---- backend.save_step: chain[it] = coords ; log_prob[it] = lp -----------------------------
     // (no barrier needed in between: the next reader of list_next / coords is behind the barrier
