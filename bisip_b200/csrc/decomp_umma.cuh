@@ -37,9 +37,13 @@ static_assert(kThreads == 256, "decomp_umma.cuh maps 256 threads onto 128 TMEM l
 #endif
 constexpr int kUmmaRows = 128;      // MMA M: proposals per tile (>= rows of a half-step: W <= 256)
 constexpr int kUmmaChunk = 64;      // taus per A buffer
-// The FP32 epilogue expands the residual about R0 = kUmmaR0c: (y - R0 delta)/sigma = c0 - (R0 - kUmmaR0c) delta/sigma.
-// BISIP normalises every spectrum by max|Z| (utils.py:138-142) and bounds r0 to [0.9, 1.1] (models.py:212), so the
-// second term is a small correction whose FP32 rounding (|R0 - 1| * 6e-8 / sigma) stays below the accumulators' own.
+// The residual constant (y - R0 delta)/sigma is produced by the tensor core as well: expanded about R0 = kUmmaR0c,
+//   (y - R0 delta)/sigma = c0 - dR0 g,   c0 = (y - kUmmaR0c delta)/sigma,  g = delta/sigma,  dR0 = R0 - kUmmaR0c,
+// it is one extra K step of 8 products  [1, 1, 1, -d_hi, -d_hi, -d_mid, -d_mid, -d_lo] x [c0_hi, c0_mid, c0_lo, g_hi,
+// g_mid, g_hi, g_mid, g_hi]  (three-way TF32 splits: c0 enters exactly to 2^-33, the product to ~2^-22 of |dR0 g|)
+// that initialises the accumulators, so the epilogue is a bare sum of squares.  BISIP normalises every spectrum by
+// max|Z| (utils.py:138-142) and bounds r0 to [0.9, 1.1] (models.py:212): |dR0| <= 0.1 and the dropped cross terms
+// (~2e-6 for sigma = 1 %) stay below the FP32 accumulators' own rounding of the O(10-50) partial sums.
 constexpr double kUmmaR0c = 1.0;
 
 struct DecompUmmaShape {
@@ -52,7 +56,10 @@ struct DecompUmmaShape {
   __host__ __device__ DecompUmmaShape(int n, int s, int d)
       : N(n), S(s), D(d), NCH(ceil_div(n, 16) * 16), NC(2 * ceil_div(n, 16) * 16), SP(ceil_div(s, 8) * 8),
         SQ(ceil_div(s, 16) * 16), nchunks(ceil_div(ceil_div(s, 8) * 8, kUmmaChunk)) {}
-  __host__ __device__ size_t plane_bytes() const { return (size_t)NC * SP * 4; }    // one K/sigma plane
+  __host__ __device__ size_t plane_bytes() const { return (size_t)NC * SP * 4; }    // K/sigma lo plane
+  // hi plane: one more K step of 8 columns holding the residual constants (see the epilogue note below)
+  __host__ __device__ size_t hiplane_bytes() const { return (size_t)NC * (SP + 8) * 4; }
+  __host__ __device__ size_t lk_bytes() const { return SQ * 64 > 4096 ? (size_t)SQ * 64 : 4096; }   // also holds A_ext (4 KB)
   __host__ __device__ size_t qplane_bytes() const { return (size_t)SQ * 32; }       // one Q plane: SQ taus x 8 coefficients
   __host__ __device__ int tmem_cols() const { return nchunks > 1 ? 512 : 256; }
   __host__ __device__ static bool fits(int n_freq, int n_tau) { return n_freq <= 64 && n_tau <= 512; }
@@ -60,11 +67,12 @@ struct DecompUmmaShape {
 
 // Shared-memory block of the evaluator.  Only the base pointer is kept (the sampler kernel is register-bound at two
 // CTAs per SM); the sub-arrays are addressed by offsets recomputed from the shape:
-//   Bhi  [NC x SP] TF32, canonical K-major core matrices (8 columns x 16 bytes);  Blo the same (PREC == 3)
+//   Bhi  [NC x (SP + 8)] TF32, canonical K-major core matrices (8 columns x 16 bytes); K step SP/8 = residual constants
+//   Blo  [NC x SP] the low plane (PREC == 3)
 //   Q    [3][SQ x 8] TF32 planes of the orthonormalised tau basis (stage-1 B operand)
-//   Lk   [SQ][8] doubles: init scratch, log_tau powers per tau, orthonormalised in place
+//   Lk   [SQ][8] doubles: init scratch, log_tau powers per tau, orthonormalised in place; afterwards its first 4 KB
+//        hold A_ext [128 rows x 8] TF32, the per-proposal A operand of the residual-constant K step
 //   R    [8][8] doubles:  L_i = sum_{j<=i} R[i][j] q_j
-//   col  [NC] float4 {c0_hi, c0_lo, delta/sigma, -}: c0 = (y - kUmmaR0c delta)/sigma as a two-float pair
 //   part [128] doubles: partial chi^2 of the imaginary half
 //   bar  [5] mbarriers (stage-1 MMAs, column blocks of the stage-2 MMAs; 3 in use);  tmem: base address from tcgen05.alloc
 struct DecompUmmaSmem {
@@ -77,16 +85,15 @@ struct DecompUmmaSmem {
 #endif
 };
 struct DecompUmmaOff {
-  uint32_t Blo, Q, Lk, R, col, part, bar, tmem;
+  uint32_t Blo, Q, Lk, R, part, bar, tmem;
   template <int PREC>
   static __device__ __forceinline__ DecompUmmaOff make(const DecompUmmaShape& sh) {
     DecompUmmaOff o;
-    o.Blo = (uint32_t)sh.plane_bytes();
-    o.Q = o.Blo * (PREC == 3 ? 2u : 1u);
+    o.Blo = (uint32_t)sh.hiplane_bytes();
+    o.Q = o.Blo + (PREC == 3 ? (uint32_t)sh.plane_bytes() : 0u);
     o.Lk = o.Q + 3u * (uint32_t)sh.qplane_bytes();
-    o.R = o.Lk + (uint32_t)sh.SQ * 64u;
-    o.col = o.R + 512u;
-    o.part = o.col + (uint32_t)sh.NC * 16u;
+    o.R = o.Lk + (uint32_t)sh.lk_bytes();
+    o.part = o.R + 512u;
     o.bar = o.part + kUmmaRows * 8u;
     o.tmem = o.bar + 40u;
     return o;
@@ -95,7 +102,7 @@ struct DecompUmmaOff {
 
 __host__ __device__ inline size_t decomp_umma_smem_doubles(const DecompUmmaShape& sh, int prec) {
   const size_t planes = prec == 3 ? 2 : 1;
-  return 16 + planes * sh.plane_bytes() / 8 + 3 * sh.qplane_bytes() / 8 + (size_t)sh.SQ * 8 + 64 + 2 * (size_t)sh.NC +
+  return 16 + (sh.hiplane_bytes() + (planes - 1) * sh.plane_bytes() + 3 * sh.qplane_bytes() + sh.lk_bytes()) / 8 + 64 +
          kUmmaRows + 8;
 }
 
@@ -130,6 +137,13 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tD, uint32_t tA, uint64_t 
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tD), "r"(tA), "l"(bdesc), "r"(idesc),
+      "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ss(uint32_t tD, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tD), "l"(adesc), "l"(bdesc), "r"(idesc),
       "r"(accumulate)
       : "memory");
 }
@@ -205,10 +219,9 @@ __device__ inline void decomp_umma_init(DecompUmmaSmem& s, const DecompUmmaShape
   const int tid = threadIdx.x, lane = tid & 31;
   const int N = sh.N, S = sh.S, SP = sh.SP, NCH = sh.NCH, D = sh.D;
   const DecompUmmaOff o = DecompUmmaOff::make<PREC>(sh);
-  struct { uint8_t *Bhi, *Blo, *Q; double *Lk, *R; float4* col; uint64_t* bar; uint32_t* tmem; } l;
+  struct { uint8_t *Bhi, *Blo, *Q; double *Lk, *R; uint64_t* bar; uint32_t* tmem; } l;
   l.Bhi = s.p0; l.Blo = s.p0 + o.Blo; l.Q = s.p0 + o.Q;
   l.Lk = reinterpret_cast<double*>(s.p0 + o.Lk); l.R = reinterpret_cast<double*>(s.p0 + o.R);
-  l.col = reinterpret_cast<float4*>(s.p0 + o.col);
   l.bar = reinterpret_cast<uint64_t*>(s.p0 + o.bar); l.tmem = reinterpret_cast<uint32_t*>(s.p0 + o.tmem);
   if (tid < 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(l.tmem)), "r"(sh.tmem_cols())
@@ -221,7 +234,7 @@ __device__ inline void decomp_umma_init(DecompUmmaSmem& s, const DecompUmmaShape
   }
   {
     uint32_t* z = reinterpret_cast<uint32_t*>(l.Bhi);      // K/sigma planes and the Q planes are contiguous
-    const int nw = (int)((sh.plane_bytes() * (PREC == 3 ? 2 : 1) + 3 * sh.qplane_bytes()) / 4);
+    const int nw = (int)(o.Lk / 4);
     for (int i = tid; i < nw; i += kThreads) z[i] = 0u;
   }
   for (int i = tid; i < sh.SQ * 8; i += kThreads) {
@@ -231,20 +244,8 @@ __device__ inline void decomp_umma_init(DecompUmmaSmem& s, const DecompUmmaShape
   if (tid < 64) l.R[tid] = 0.0;
   const bool scaled = (y != nullptr);
   double csum = 0.0;
-  for (int n = tid; n < sh.NC; n += kThreads) {
-    const int part = n >= NCH, j = n - part * NCH;
-    double ys = 0.0, ds = 0.0;
-    if (j < N && scaled) {
-      const double e = yerr[part * N + j];
-      const double is = 1.0 / e;
-      ys = y[part * N + j] * is;
-      ds = part ? 0.0 : is;
-      csum += 2.0 * log(e * e);
-    }
-    const double c0 = ys - kUmmaR0c * ds;
-    const float c0h = (float)c0;
-    l.col[n] = make_float4(c0h, (float)(c0 - (double)c0h), (float)ds, 0.f);
-  }
+  for (int c = tid; c < 2 * N; c += kThreads)
+    if (scaled) csum += 2.0 * log(yerr[c] * yerr[c]);
   __syncthreads();
   // ---- warp 0: orthonormalise the D rows of the tau table in place (modified Gram-Schmidt, every projection twice);
   //      the other warps build the K/sigma planes meanwhile -----------------------------------------------------
@@ -271,6 +272,22 @@ __device__ inline void decomp_umma_init(DecompUmmaSmem& s, const DecompUmmaShape
       __syncwarp();
     }
   } else {
+    const int sbo_hi = 32 * (SP + 8);
+    // residual constants: K step SP/8 of the hi plane, column n: [c0_hi, c0_mid, c0_lo, g_hi, g_mid, g_hi, g_mid, g_hi]
+    for (int n = tid - 32; n < sh.NC; n += kThreads - 32) {
+      const int part = n >= NCH, j = n - part * NCH;
+      double c0 = 0.0, g = 0.0;
+      if (j < N && scaled) {
+        const double is = 1.0 / yerr[part * N + j];
+        g = part ? 0.0 : is;
+        c0 = y[part * N + j] * is - kUmmaR0c * g;
+      }
+      uint32_t c[3], q[3];
+      split3_tf32(c0, c[0], c[1], c[2]);
+      split3_tf32(g, q[0], q[1], q[2]);
+      const uint32_t ext[8] = {c[0], c[1], c[2], q[0], q[1], q[0], q[1], q[0]};
+      for (int e = 0; e < 8; ++e) *reinterpret_cast<uint32_t*>(l.Bhi + umma_tile_off(n, SP + e, sbo_hi)) = ext[e];
+    }
     double cs, sn;
     sincospi(0.5 * c_exp, &sn, &cs);
     for (int i = tid - 32; i < S * N; i += kThreads - 32) {
@@ -283,10 +300,10 @@ __device__ inline void decomp_umma_init(DecompUmmaSmem& s, const DecompUmmaShape
       }
       uint32_t hi, lo;
       split2_tf32((float)kre, hi, lo);
-      *reinterpret_cast<uint32_t*>(l.Bhi + umma_tile_off(j, k, 32 * SP)) = hi;
+      *reinterpret_cast<uint32_t*>(l.Bhi + umma_tile_off(j, k, sbo_hi)) = hi;
       if (PREC == 3) *reinterpret_cast<uint32_t*>(l.Blo + umma_tile_off(j, k, 32 * SP)) = lo;
       split2_tf32((float)kim, hi, lo);
-      *reinterpret_cast<uint32_t*>(l.Bhi + umma_tile_off(NCH + j, k, 32 * SP)) = hi;
+      *reinterpret_cast<uint32_t*>(l.Bhi + umma_tile_off(NCH + j, k, sbo_hi)) = hi;
       if (PREC == 3) *reinterpret_cast<uint32_t*>(l.Blo + umma_tile_off(NCH + j, k, 32 * SP)) = lo;
     }
   }
@@ -388,8 +405,16 @@ __device__ inline void decomp_umma_eval(DecompUmmaSmem& s, const DecompUmmaShape
     tmem_st4(tB + lane_base + 8 + 4 * h, p1);
     UMMA_MARK(7)
     tmem_st4(tB + lane_base + 16 + 4 * h, p2);
+    if (h == 1) {     // A_ext row r = [1, 1, 1, -d_hi, -d_hi, -d_mid, -d_mid, -d_lo], d = R0 - kUmmaR0c (shared memory, SS-mode MMA)
+      uint32_t d0, d1, d2;
+      split3_tf32(r < nrows ? kUmmaR0c - R0 : 0.0, d0, d1, d2);
+      const uint32_t ax = sb + o.Lk + (uint32_t)umma_tile_off(r, 0, 256);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ax), "r"(0x3f800000u), "r"(0x3f800000u), "r"(0x3f800000u), "r"(d0) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ax + 128u), "r"(d0), "r"(d1), "r"(d1), "r"(d2) : "memory");
+    }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // A_ext -> visible to the tensor core
   tc_fence_before();
   __syncthreads();
   UMMA_MARK(0)
@@ -455,14 +480,16 @@ __device__ inline void decomp_umma_eval(DecompUmmaSmem& s, const DecompUmmaShape
       if (elect_one()) {
         for (int blk = 0; blk < nblk; ++blk) {
           const int n0 = (blk & 1) * sh.NCH + (blk >> 1) * bw;           // first column of the block
-          const uint32_t boff = (uint32_t)(n0 >> 3) * (uint32_t)(32 * sh.SP) + 32u * k0;
-          const uint64_t dhi = umma_desc(sb + boff, 32 * sh.SP), dlo = umma_desc(sb + o.Blo + boff, 32 * sh.SP);
-          uint32_t acc = c > 0 ? 1u : 0u;
+          const int sbo_hi = 32 * (sh.SP + 8), sbo_lo = 32 * sh.SP;
+          const uint32_t rhi = (uint32_t)(n0 >> 3) * (uint32_t)sbo_hi, rlo = (uint32_t)(n0 >> 3) * (uint32_t)sbo_lo;
+          const uint64_t dhi = umma_desc(sb + rhi + 32u * k0, sbo_hi), dlo = umma_desc(sb + o.Blo + rlo + 32u * k0, sbo_lo);
+          // the residual constants initialise the accumulators (K step SP/8 of the hi plane x A_ext from shared memory)
+          if (c == 0) umma_tf32_ss(tD + n0, umma_desc(sb + o.Lk, 256), umma_desc(sb + rhi + 32u * sh.SP, sbo_hi), idescb, 0u);
           if (PREC == 3) {
-            for (int j = 0; j < ng; ++j) { umma_tf32_ts(tD + n0, tA + 64 + 8 * j, dhi + 16u * j, idescb, acc); acc = 1u; }
+            for (int j = 0; j < ng; ++j) umma_tf32_ts(tD + n0, tA + 64 + 8 * j, dhi + 16u * j, idescb, 1u);
             for (int j = 0; j < ng; ++j) umma_tf32_ts(tD + n0, tA + 8 * j, dlo + 16u * j, idescb, 1u);
           }
-          for (int j = 0; j < ng; ++j) { umma_tf32_ts(tD + n0, tA + 8 * j, dhi + 16u * j, idescb, acc); acc = 1u; }
+          for (int j = 0; j < ng; ++j) umma_tf32_ts(tD + n0, tA + 8 * j, dhi + 16u * j, idescb, 1u);
           if (c + 1 == sh.nchunks) umma_commit(barD + 8 * blk);
         }
       }
@@ -471,11 +498,9 @@ __device__ inline void decomp_umma_eval(DecompUmmaSmem& s, const DecompUmmaShape
   }
   UMMA_MARK(3)
   // ---- epilogue: D row r; half h owns column block h (columns [h NCH, (h+1) NCH)) --------------------------------
-  // The accumulators are FP32, so the residual is formed in FP32 too: res = c0 - dR0 * delta/sigma + D with c0 a
-  // two-float constant per column (see kUmmaR0c), which keeps its error below the accumulators' own rounding.
+  // The accumulators already hold the weighted residual (y - Z)/sigma (see kUmmaR0c): chi^2 is their sum of squares.
   double acc = 0.0;
   {
-    const float dR0 = (float)(R0 - kUmmaR0c);
     float ch[4] = {0.f, 0.f, 0.f, 0.f};
     for (int i = 0; i < nblk / 2; ++i) {
       const int blk = h + 2 * i;
@@ -497,14 +522,9 @@ __device__ inline void decomp_umma_eval(DecompUmmaSmem& s, const DecompUmmaShape
             }
           }
         } else {
-          const uint32_t ca = sb + o.col + (uint32_t)(h * sh.NCH + i * bw + c0) * 16u;
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            float c0h, c0l, dsg, unused;
-            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c0h), "=f"(c0l), "=f"(dsg), "=f"(unused) : "r"(ca + e * 16));
-            const float d = __uint_as_float(v[e]);
-            const float head = h == 0 ? fmaf(-dR0, dsg, c0h) : c0h;          // imaginary columns: delta = 0
-            const float res = (head + d) + c0l;
+            const float res = __uint_as_float(v[e]);
             ch[e & 3] = fmaf(res, res, ch[e & 3]);
           }
         }
