@@ -17,6 +17,7 @@ mean / std summary, and for N>1 the NCCL all-gather of the summaries.
 `roofline`: ensemble_decomp kernel (the dominant launch): algorithmic flops (17,792 per eval,
            SURVEY.md §8d) / its CUDA-event duration, against the FP64 DMMA peak measured on this
            box by tools/peaks (MEASURED_PEAKS.json has no FP64 figure).
+`variants`: the TF32 / 3xTF32 tcgen05 kernels on a slice of the same shard (kernel alone), next to the FP64 numbers.
 `cpu_baseline`: the reference's own Cython + NumPy log-probability (oracle/_ref) under the emcee
            restatement, on all host cores, on a bounded sample of the same spectra.
 `--impl reference`: that CPU arm alone, as its own JSON line.
@@ -292,6 +293,31 @@ def run_gpu(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = evals_step / (float(te.item()) * 1e-3)
 
+    # ---- reduced-precision variants of the same workload (north_star: "a TF32/3xTF32 variant compared against it"):
+    #      the tcgen05 kernel on a 592-spectra slice of this rank's shard, ensemble kernel alone, CUDA events.
+    #      Reported next to the FP64 numbers; `value`, `e2e` and `roofline` stay FP64.
+    variants = {}
+    if rank == 0:
+        nv = min(B, 592)
+        for prec in ("3xtf32", "tf32"):
+            alt = BatchInversion('decomp', syn['w'], zn_h[:nv], ze_h[:nv], nwalkers=WALKERS, nsteps=NSTEPS, poly_deg=POLY_DEG,
+                                 n_tau=N_TAU, seed=SEED, spectrum_offset=b0, device=dev, precision=prec)
+            aspec = alt._spec()
+            best = 1e30
+            for rep in range(3):
+                c = p0_d[:nv].clone()
+                ev[2].record()
+                r_alt = engine.ensemble_run(aspec, c, w_d, y_d[:nv], ye_d[:nv], bounds_d, nsteps=500, seed=SEED, spectrum0=b0,
+                                            discard=250, thin=10, store_chain=True, store_logp=False)
+                ev[3].record()
+                torch.cuda.synchronize()
+                if rep:
+                    best = min(best, ev[2].elapsed_time(ev[3]))
+            variants[prec] = {"kernel": engine.decomp_kernel_kind(aspec, N_FREQ, WALKERS), "evals_per_s": nv * WALKERS * 501 / (best * 1e-3),
+                              "spectra": nv, "steps": 500, "kernel_ms": best,
+                              "acceptance_fraction": float(r_alt['accepted'].double().mean().item() / 500),
+                              "nan_flags": int((r_alt['flags'] != 0).sum().item())}
+            del r_alt
     if rank == 0:
         k_ms = float(np.mean(kern_ms))
         flops_launch = FLOP_PER_EVAL * float(B) * WALKERS * (NSTEPS + 1)       # +1: log-prob of p0
@@ -332,6 +358,9 @@ def run_gpu(args):
                              "wall_s": cpu_wall,
                              "note": "reference models.py + Cython (oracle/_ref) under oracle/emcee_restatement.py"},
             "clocks": clk, "acceptance_fraction": acc, "nan_flags": flags_bad,
+            "variants": {"note": "reduced-precision decomposition kernels on a slice of the same shard (ensemble kernel alone); "
+                                 "tolerances in profiles/r01f_tf32_study.md; value / e2e / roofline above are FP64",
+                         "fp64_evals_per_s_kernel": evals_step / world * (NSTEPS + 1) / NSTEPS / (k_ms * 1e-3), **variants},
         }
         print(json.dumps(line))
     if world > 1:
