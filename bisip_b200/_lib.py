@@ -23,7 +23,7 @@ EXPORTS = ("bisip_abi_version", "bisip_last_error", "bisip_launch_count", "bisip
            "bisip_log_probability", "bisip_decomp_build_kernel", "bisip_n_keep",
            "bisip_ensemble_run", "bisip_column_stats_workspace", "bisip_column_stats",
            "bisip_decomp_kernel_kind")
-KERNEL_KINDS = {0: "dmma", 1: "dmma-cluster", 2: "mma-tf32", 3: "tcgen05"}
+KERNEL_KINDS = {0: "dmma", 1: "dmma-cluster", 2: "mma-tf32", 3: "tcgen05", 4: "tcgen05-cluster"}
 
 
 class BisipError(RuntimeError):

@@ -274,15 +274,25 @@ bool use_rc(const bisip_model_desc& d) {
 // n_tau <= 64: 256 tensor-memory columns per CTA, two CTAs per SM — the request is padded so that a third CTA
 // (which would spin in tcgen05.alloc) never becomes resident.  n_tau > 64: 512 columns, so the request is padded
 // past half an SM's shared memory and exactly one CTA is resident.
-struct UmmaPlan { bool ok; bool two_per_sm; size_t smem; };
-UmmaPlan plan_umma(const bisip_model_desc& d, size_t other_bytes, int rows) {
-  UmmaPlan pl{false, false, 0};
+struct UmmaPlan { bool ok; bool two_per_sm; size_t smem; bool cluster; };
+UmmaPlan plan_umma(const bisip_model_desc& d, size_t other_bytes, int rows, bool allow_cluster = false) {
+  UmmaPlan pl{false, false, 0, false};
   const int planes = prec_planes(d.precision);
   if (d.model != BISIP_MODEL_DECOMP || (d.precision != BISIP_PREC_TF32 && d.precision != BISIP_PREC_3XTF32)) return pl;
   if (rows > kUmmaRows || !DecompUmmaShape::fits(d.n_freq, d.n_tau)) return pl;
   const DecompUmmaShape sh(d.n_freq, d.n_tau, d.n_coef);
   size_t smem = other_bytes + decomp_umma_smem_doubles(sh, planes) * 8;
-  if (smem > (size_t)device_smem_optin()) return pl;
+  if (smem > (size_t)device_smem_optin()) {
+    // K planes too large for one CTA: a 2-CTA cluster splits the real | imaginary columns (sampler kernel only)
+    if (!allow_cluster) return pl;
+    const DecompUmmaShape shc(d.n_freq, d.n_tau, d.n_coef, 1, 0);
+    smem = other_bytes + decomp_umma_smem_doubles(shc, planes) * 8;
+    if (smem > (size_t)device_smem_optin()) return pl;
+    pl.ok = true;
+    pl.cluster = true;
+    pl.smem = smem < 116 * 1024 ? 116 * 1024 : smem;      // 512 tensor-memory columns: one CTA per SM
+    return pl;
+  }
   pl.ok = true;
   pl.two_per_sm = sh.nchunks == 1 && smem <= 113 * 1024;
   const size_t floor_bytes = pl.two_per_sm ? 77 * 1024 : 116 * 1024;
@@ -469,7 +479,10 @@ int bisip_decomp_kernel_kind(const bisip_model_desc* desc, int n_walkers) {
   if (int rc = check_desc(desc)) return rc;
   if (desc->model != BISIP_MODEL_DECOMP || n_walkers < 2) return fail(BISIP_ERR_BAD_ARG, "bisip_decomp_kernel_kind: bad argument");
   const size_t other = sampler_smem_bytes(n_walkers, desc->ndim);
-  if (plan_umma(*desc, other, (n_walkers + 1) / 2).ok) return BISIP_KERNEL_TCGEN05;
+  {
+    const UmmaPlan up = plan_umma(*desc, other, (n_walkers + 1) / 2, true);
+    if (up.ok) return up.cluster ? BISIP_KERNEL_TCGEN05_CLUSTER : BISIP_KERNEL_TCGEN05;
+  }
   if (!use_rc(*desc)) return BISIP_KERNEL_DMMA;
   RcPlan plan;
   if (int rc = plan_rc(*desc, other, sampler_rows_pad(n_walkers), &plan)) return rc;
@@ -568,7 +581,14 @@ int bisip_ensemble_run(const bisip_model_desc* desc, int n_spectra, int n_walker
       return launch_vec_ensemble<ShinRow, 6>(P, grid, smem, st, "ensemble_shin");
     default: {
       {
-        const UmmaPlan up = plan_umma(*desc, smem, (n_walkers + 1) / 2);
+        const UmmaPlan up = plan_umma(*desc, smem, (n_walkers + 1) / 2, true);
+        if (up.ok && up.cluster) {
+          if ((long long)n_spectra * 2 > 2147483647LL) return fail(BISIP_ERR_UNSUPPORTED, "too many spectra per call");
+          const dim3 g(n_spectra * 2);
+          return prec_planes(desc->precision) == 3
+                     ? launch_cluster(ensemble_kernel<DecompUmmaEvaluator<3, true>, 1>, g, 2, up.smem, st, "ensemble_decomp_umma_3xtf32_cluster", &P)
+                     : launch_cluster(ensemble_kernel<DecompUmmaEvaluator<1, true>, 1>, g, 2, up.smem, st, "ensemble_decomp_umma_tf32_cluster", &P);
+        }
         if (up.ok) {
           const bool x3 = prec_planes(desc->precision) == 3;
           if (up.two_per_sm)

@@ -24,6 +24,7 @@
 // Restates reference Decomp_cyth (cython_funcs.pyx:75-94) + _log_likelihood (models.py:59-62) at TF32 precision.
 #pragma once
 #include "decomp_eval.cuh"
+#include "decomp_rc.cuh"   // cooperative-groups cluster handle (cg::)
 
 namespace bisip {
 
@@ -49,12 +50,15 @@ constexpr double kUmmaR0c = 1.0;
 struct DecompUmmaShape {
   int N, S, D;
   int NCH;     // columns per part (real | imag), multiple of 16
-  int NC;      // stage-2 MMA N = 2 NCH, multiple of 32, <= 128
+  int NC;      // columns held by this CTA = stage-2 MMA N: 2 NCH, or NCH when a 2-CTA cluster splits real | imag
+  int cl;      // 1: cluster mode (K planes too large for one CTA): CTA `part` of the pair owns the real (0) or imaginary (1) columns
+  int part;
   int SP;      // taus padded to a multiple of 8 (stage-2 K steps)
   int SQ;      // taus padded to a multiple of 16 (stage-1 MMA N)
   int nchunks; // chunks of <= 64 taus
-  __host__ __device__ DecompUmmaShape(int n, int s, int d)
-      : N(n), S(s), D(d), NCH(ceil_div(n, 16) * 16), NC(2 * ceil_div(n, 16) * 16), SP(ceil_div(s, 8) * 8),
+  __host__ __device__ DecompUmmaShape(int n, int s, int d, int cluster = 0, int rank = 0)
+      : N(n), S(s), D(d), NCH(ceil_div(n, 16) * 16), NC((cluster ? 1 : 2) * ceil_div(n, 16) * 16), cl(cluster), part(rank),
+        SP(ceil_div(s, 8) * 8),
         SQ(ceil_div(s, 16) * 16), nchunks(ceil_div(ceil_div(s, 8) * 8, kUmmaChunk)) {}
   __host__ __device__ size_t plane_bytes() const { return (size_t)NC * SP * 4; }    // K/sigma lo plane
   // hi plane: one more K step of 8 columns holding the residual constants (see the epilogue note below)
@@ -73,19 +77,19 @@ struct DecompUmmaShape {
 //   Lk   [SQ][8] doubles: init scratch, log_tau powers per tau, orthonormalised in place; afterwards its first 4 KB
 //        hold A_ext [128 rows x 8] TF32, the per-proposal A operand of the residual-constant K step
 //   R    [8][8] doubles:  L_i = sum_{j<=i} R[i][j] q_j
-//   part [128] doubles: partial chi^2 of the imaginary half
+//   part [128] doubles: partial chi^2 of the second thread half;  xsum [2][128] (cluster mode): this CTA's chi^2 for the peer
 //   bar  [5] mbarriers (stage-1 MMAs, column blocks of the stage-2 MMAs; 3 in use);  tmem: base address from tcgen05.alloc
 struct DecompUmmaSmem {
   uint8_t* p0;        // 128-byte aligned start (= Bhi)
   double llconst;
   uint32_t tbase;
-  uint32_t phase;     // bit i: parity of the next completion of bar[i]
+  uint32_t phase;     // bit i: parity of the next completion of bar[i]; bit 8: buffer of the cluster exchange
 #ifdef BISIP_PHASE_TIMING
   long long ph[8];    // per-thread cycle counters of the evaluation sub-phases (registers)
 #endif
 };
 struct DecompUmmaOff {
-  uint32_t Blo, Q, Lk, R, part, bar, tmem;
+  uint32_t Blo, Q, Lk, R, part, xsum, bar, tmem;
   template <int PREC>
   static __device__ __forceinline__ DecompUmmaOff make(const DecompUmmaShape& sh) {
     DecompUmmaOff o;
@@ -94,7 +98,8 @@ struct DecompUmmaOff {
     o.Lk = o.Q + 3u * (uint32_t)sh.qplane_bytes();
     o.R = o.Lk + (uint32_t)sh.lk_bytes();
     o.part = o.R + 512u;
-    o.bar = o.part + kUmmaRows * 8u;
+    o.xsum = o.part + kUmmaRows * 8u;
+    o.bar = o.xsum + (sh.cl ? 2u * kUmmaRows * 8u : 0u);
     o.tmem = o.bar + 40u;
     return o;
   }
@@ -103,7 +108,7 @@ struct DecompUmmaOff {
 __host__ __device__ inline size_t decomp_umma_smem_doubles(const DecompUmmaShape& sh, int prec) {
   const size_t planes = prec == 3 ? 2 : 1;
   return 16 + (sh.hiplane_bytes() + (planes - 1) * sh.plane_bytes() + 3 * sh.qplane_bytes() + sh.lk_bytes()) / 8 + 64 +
-         kUmmaRows + 8;
+         kUmmaRows + (sh.cl ? 2 * kUmmaRows : 0) + 8;
 }
 
 template <int PREC>
@@ -281,7 +286,7 @@ __device__ inline void decomp_umma_init(DecompUmmaSmem& s, const DecompUmmaShape
     const int sbo_hi = 32 * (SP + 8);
     // residual constants: K step SP/8 of the hi plane, column n: [c0_hi, c0_mid, c0_lo, g_hi, g_mid, g_hi, g_mid, g_hi]
     for (int n = tid - 32; n < sh.NC; n += kThreads - 32) {
-      const int part = n >= NCH, j = n - part * NCH;
+      const int part = sh.cl ? sh.part : (n >= NCH), j = sh.cl ? n : n - part * NCH;
       double c0 = 0.0, g = 0.0;
       if (j < N && scaled) {
         const double is = 1.0 / yerr[part * N + j];
@@ -305,12 +310,17 @@ __device__ inline void decomp_umma_init(DecompUmmaSmem& s, const DecompUmmaShape
         kim *= 1.0 / yerr[N + j];
       }
       uint32_t hi, lo;
-      split2_tf32((float)kre, hi, lo);
-      *reinterpret_cast<uint32_t*>(l.Bhi + umma_tile_off(j, k, sbo_hi)) = hi;
-      if (PREC == 3) *reinterpret_cast<uint32_t*>(l.Blo + umma_tile_off(j, k, 32 * SP)) = lo;
-      split2_tf32((float)kim, hi, lo);
-      *reinterpret_cast<uint32_t*>(l.Bhi + umma_tile_off(NCH + j, k, sbo_hi)) = hi;
-      if (PREC == 3) *reinterpret_cast<uint32_t*>(l.Blo + umma_tile_off(NCH + j, k, 32 * SP)) = lo;
+      if (!sh.cl || sh.part == 0) {
+        split2_tf32((float)kre, hi, lo);
+        *reinterpret_cast<uint32_t*>(l.Bhi + umma_tile_off(j, k, sbo_hi)) = hi;
+        if (PREC == 3) *reinterpret_cast<uint32_t*>(l.Blo + umma_tile_off(j, k, 32 * SP)) = lo;
+      }
+      if (!sh.cl || sh.part == 1) {
+        const int n = sh.cl ? j : NCH + j;
+        split2_tf32((float)kim, hi, lo);
+        *reinterpret_cast<uint32_t*>(l.Bhi + umma_tile_off(n, k, sbo_hi)) = hi;
+        if (PREC == 3) *reinterpret_cast<uint32_t*>(l.Blo + umma_tile_off(n, k, 32 * SP)) = lo;
+      }
     }
   }
   __syncthreads();
@@ -426,7 +436,7 @@ __device__ inline void decomp_umma_eval(DecompUmmaSmem& s, const DecompUmmaShape
   UMMA_MARK(0)
   // stage-2 column blocks: the real and the imaginary columns (N = NCH each).  Measured on B200 (C5 shape, 3xTF32):
   // one N = 128 block 5.36e9 evals/s, two blocks 6.00e9, four N = 32 blocks 5.11e9 (short instructions pay a fixed cost).
-  const int nblk = 2, bw = sh.NCH;
+  const int nblk = sh.cl ? 1 : 2, bw = sh.NCH;
   const uint32_t idescb = umma_idesc(bw);
   const uint32_t q0a = sb + o.Q, qpb = (uint32_t)sh.qplane_bytes();
   for (int c = 0; c < sh.nchunks; ++c) {
@@ -485,7 +495,7 @@ __device__ inline void decomp_umma_eval(DecompUmmaSmem& s, const DecompUmmaShape
       tc_fence_after();
       if (elect_one()) {
         for (int blk = 0; blk < nblk; ++blk) {
-          const int n0 = (blk & 1) * sh.NCH + (blk >> 1) * bw;           // first column of the block
+          const int n0 = blk * sh.NCH;                                   // first column of the block
           const int sbo_hi = 32 * (sh.SP + 8), sbo_lo = 32 * sh.SP;
           const uint32_t rhi = (uint32_t)(n0 >> 3) * (uint32_t)sbo_hi, rlo = (uint32_t)(n0 >> 3) * (uint32_t)sbo_lo;
           const uint64_t dhi = umma_desc(sb + rhi + 32u * k0, sbo_hi), dlo = umma_desc(sb + o.Blo + rlo + 32u * k0, sbo_lo);
@@ -503,19 +513,22 @@ __device__ inline void decomp_umma_eval(DecompUmmaSmem& s, const DecompUmmaShape
     }
   }
   UMMA_MARK(3)
-  // ---- epilogue: D row r; half h owns column block h (columns [h NCH, (h+1) NCH)) --------------------------------
+  // ---- epilogue: D row r; half h owns column block h (columns [h NCH, (h+1) NCH)); in cluster mode the CTA has one
+  //      block and the halves share it (when NCH/2 is still a multiple of the 16-column load) ---------------------------
   // The accumulators already hold the weighted residual (y - Z)/sigma (see kUmmaR0c): chi^2 is their sum of squares.
   double acc = 0.0;
   {
+    const int blk = sh.cl ? 0 : h;
+    const bool halves = sh.cl && (sh.NCH & 31) == 0;
+    const int cw = !sh.cl ? sh.NCH : (halves ? sh.NCH / 2 : (h == 0 ? sh.NCH : 0));      // columns of this thread
+    const int cfirst = !sh.cl ? h * sh.NCH : (halves ? h * (sh.NCH / 2) : 0);
+    mbar_wait(barD + 8 * blk, (s.phase >> (1 + blk)) & 1u);
+    s.phase ^= 2u << blk;
+    tc_fence_after();
     float ch[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int i = 0; i < nblk / 2; ++i) {
-      const int blk = h + 2 * i;
-      mbar_wait(barD + 8 * blk, (s.phase >> (1 + blk)) & 1u);
-      s.phase ^= 2u << blk;
-      tc_fence_after();
-      if (!warp_live) continue;
-      const uint32_t td = tD + lane_base + (uint32_t)(h * sh.NCH + i * bw);
-      for (int c0 = 0; c0 < bw; c0 += 16) {
+    if (warp_live) {
+      const uint32_t td = tD + lane_base + (uint32_t)cfirst;
+      for (int c0 = 0; c0 < cw; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(td + c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -523,7 +536,7 @@ __device__ inline void decomp_umma_eval(DecompUmmaSmem& s, const DecompUmmaShape
           if (r < nrows) {
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
-              const int j = i * bw + c0 + e;
+              const int j = c0 + e;
               if (j < sh.N) Zout[(size_t)r * 2 * sh.N + h * sh.N + j] = (h ? 0.0 : R0) - (double)__uint_as_float(v[e]);
             }
           }
@@ -544,7 +557,18 @@ __device__ inline void decomp_umma_eval(DecompUmmaSmem& s, const DecompUmmaShape
     double* part = reinterpret_cast<double*>(s.p0 + o.part);
     if (h == 1) part[r] = acc;
     __syncthreads();
-    if (h == 0 && r < nrows) chi[r] = acc + part[r];
+    if (!sh.cl) {
+      if (h == 0 && r < nrows) chi[r] = acc + part[r];
+    } else {
+      // both CTAs of the pair run the sampler on identical walkers: exchange the per-proposal partial sums through
+      // distributed shared memory and add them in rank order, so both take bit-identical accept decisions
+      cg::cluster_group cluster = cg::this_cluster();
+      double* mine = reinterpret_cast<double*>(s.p0 + o.xsum) + ((s.phase >> 8) & 1u) * kUmmaRows;
+      if (h == 0) mine[r] = acc + part[r];
+      cluster.sync();
+      if (h == 0 && r < nrows) chi[r] = cluster.map_shared_rank(mine, 0)[r] + cluster.map_shared_rank(mine, 1)[r];
+      s.phase ^= 0x100u;
+    }
   }
   UMMA_MARK(5)
 }

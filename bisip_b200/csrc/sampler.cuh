@@ -411,16 +411,16 @@ struct DecompTF32Evaluator {
 
 // TF32 (PREC=1) / 3xTF32 (PREC=3) stage 2 on tcgen05 tensor cores: A (chargeability) and the FP32 accumulators
 // live in tensor memory, one M = 128 tile per half-step (<= 256 walkers, <= 64 frequencies).
-template <int PREC>
+template <int PREC, bool CL = false>
 struct DecompUmmaEvaluator {
-  static constexpr bool kClustered = false;
+  static constexpr bool kClustered = CL;
   static constexpr bool kNeedsPrepare = false;
   __device__ __forceinline__ void prepare_row(int, const double*) {}
   DecompUmmaSmem sm;
   DecompUmmaShape sh;
-  __device__ DecompUmmaEvaluator(const bisip_model_desc& d, int, int) : sh(d.n_freq, d.n_tau, d.n_coef) {}
+  __device__ DecompUmmaEvaluator(const bisip_model_desc& d, int, int rank) : sh(d.n_freq, d.n_tau, d.n_coef, CL ? 1 : 0, rank) {}
   static __host__ size_t smem_doubles(const bisip_model_desc& d, int) {
-    return decomp_umma_smem_doubles(DecompUmmaShape(d.n_freq, d.n_tau, d.n_coef), PREC);
+    return decomp_umma_smem_doubles(DecompUmmaShape(d.n_freq, d.n_tau, d.n_coef, CL ? 1 : 0, 0), PREC);
   }
   __device__ double* carve(double* base, int) { return decomp_umma_carve<PREC>(sm, base, sh); }
   __device__ void init(const bisip_model_desc& d, const double* w, const double* taus, const double* log_taus,

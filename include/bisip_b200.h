@@ -92,7 +92,8 @@ enum bisip_kernel_kind {
   BISIP_KERNEL_DMMA = 0,         /* FP64 mma.sync (DMMA) tiles, n_tau <= 64 */
   BISIP_KERNEL_DMMA_CLUSTER = 1, /* FP64 DMMA, stage-1 recompute, columns split over a CTA cluster (n_tau > 64) */
   BISIP_KERNEL_MMA_TF32 = 2,     /* TF32 / 3xTF32 mma.sync tiles */
-  BISIP_KERNEL_TCGEN05 = 3       /* TF32 / 3xTF32 tcgen05.mma, operands and accumulators in tensor memory */
+  BISIP_KERNEL_TCGEN05 = 3,      /* TF32 / 3xTF32 tcgen05.mma, operands and accumulators in tensor memory */
+  BISIP_KERNEL_TCGEN05_CLUSTER = 4 /* the same with the real | imaginary columns split over a 2-CTA cluster */
 };
 int bisip_decomp_kernel_kind(const bisip_model_desc *desc, int n_walkers);
 

@@ -179,7 +179,10 @@ TCGEN05_SHAPES = [  # (n_freq, n_tau, poly_deg, walkers, c_exp, precision, expec
     (64, 64, 7, 254, 1.0, '3xtf32', 'tcgen05'),      # poly_deg 7 (8 coefficients), 127-row half-steps
     (64, 128, 4, 256, 1.0, '3xtf32', 'tcgen05'),     # two 64-tau chunks: double-buffered A, one CTA per SM
     (64, 256, 4, 128, 1.0, 'tf32', 'tcgen05'),       # four chunks (C4 tau grid)
-    (64, 256, 4, 128, 1.0, '3xtf32', 'mma-tf32'),    # K planes exceed shared memory -> mma.sync tiles
+    (64, 256, 4, 128, 1.0, '3xtf32', 'tcgen05-cluster'),   # K planes exceed one CTA: real | imaginary columns over a 2-CTA cluster
+    (64, 256, 4, 256, 0.5, '3xtf32', 'tcgen05-cluster'),   # C4 shape, Warburg
+    (40, 256, 5, 100, 1.0, '3xtf32', 'tcgen05-cluster'),   # 48 columns per CTA: the thread halves do not split them
+    (64, 512, 4, 64, 1.0, '3xtf32', 'mma-tf32'),     # too large even for the pair -> mma.sync tiles
     (64, 64, 4, 258, 1.0, '3xtf32', 'mma-tf32'),     # 129-row half-steps do not fit the 128-lane tile
     (96, 64, 4, 64, 1.0, '3xtf32', 'mma-tf32'),      # 192 columns > 128
     (64, 64, 4, 256, 1.0, '3xtf32-mma', 'mma-tf32'),

@@ -153,6 +153,21 @@ def test_c_abi_exports_every_declared_symbol():
     assert all(re.search(rf'\bT {n}\b', out) for n in declared)
 
 
+def test_header_enums_match_python_constants():
+    """The ctypes layer hard-codes the enum values of include/bisip_b200.h (models, precisions, kernel kinds)."""
+    import re
+    from bisip_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'bisip_b200.h')).read()
+    val = {m.group(1): int(m.group(2)) for m in re.finditer(r'\b(BISIP_[A-Z0-9_]+)\s*=\s*(-?\d+)', hdr)}
+    assert (val['BISIP_MODEL_COLECOLE'], val['BISIP_MODEL_DIAS'], val['BISIP_MODEL_SHIN'], val['BISIP_MODEL_DECOMP']) == \
+        (_lib.MODEL_COLECOLE, _lib.MODEL_DIAS, _lib.MODEL_SHIN, _lib.MODEL_DECOMP)
+    assert _lib.PRECISIONS == {'fp64': val['BISIP_PREC_FP64'], 'tf32': val['BISIP_PREC_TF32'], '3xtf32': val['BISIP_PREC_3XTF32'],
+                               'tf32-mma': val['BISIP_PREC_TF32_MMA'], '3xtf32-mma': val['BISIP_PREC_3XTF32_MMA']}
+    assert _lib.KERNEL_KINDS == {val['BISIP_KERNEL_DMMA']: 'dmma', val['BISIP_KERNEL_DMMA_CLUSTER']: 'dmma-cluster',
+                                 val['BISIP_KERNEL_MMA_TF32']: 'mma-tf32', val['BISIP_KERNEL_TCGEN05']: 'tcgen05',
+                                 val['BISIP_KERNEL_TCGEN05_CLUSTER']: 'tcgen05-cluster'}
+
+
 def test_walkers_independent_and_autocorr():
     from bisip_b200.sampler import integrated_time, walkers_independent
     rng = np.random.default_rng(1)
