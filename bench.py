@@ -198,6 +198,8 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":     # its banner goes to stdout, next to the JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     B = SPECTRA_PER_GPU
     b0 = rank * B                                      # weak scaling: rank r owns spectra [rB, (r+1)B)
