@@ -320,6 +320,19 @@ def run_gpu(args):
                               "acceptance_fraction": float(r_alt['accepted'].double().mean().item() / 500),
                               "nan_flags": int((r_alt['flags'] != 0).sum().item())}
             del r_alt
+        # the whole shard end to end in 3xTF32 through the public API (pinned host inputs, host summaries), like `e2e`
+        alt = BatchInversion('decomp', syn['w'], zn_h, ze_h, nwalkers=WALKERS, nsteps=NSTEPS, poly_deg=POLY_DEG,
+                             n_tau=N_TAU, seed=SEED, spectrum_offset=b0, device=dev, precision='3xtf32')
+        best = 1e30
+        for rep in range(2):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r_alt = alt.fit(p0=p0_h, discard=DISCARD, thin=THIN, percentiles=PCT)
+            torch.cuda.synchronize()
+            best = min(best, time.perf_counter() - t0)
+        variants['3xtf32'].update({"e2e_evals_per_s": B * WALKERS * NSTEPS / best, "e2e_spectra_per_s": B / best,
+                                   "e2e_ms_per_step": 1e3 * best, "e2e_nan_flags": int((r_alt['flags'] != 0).sum())})
+        del r_alt, alt
     if rank == 0:
         k_ms = float(np.mean(kern_ms))
         flops_launch = FLOP_PER_EVAL * float(B) * WALKERS * (NSTEPS + 1)       # +1: log-prob of p0
