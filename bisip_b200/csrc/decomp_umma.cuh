@@ -12,14 +12,20 @@
 //   stage 2  D[128][NC] = M x (K / sigma).  M is read back (tcgen05.ld), split into TF32 hi / lo planes and stored
 //            to tensor memory as the A operand; B = K/sigma sits in shared memory as hi / lo planes in the
 //            canonical K-major no-swizzle core-matrix layout; PREC = 3 issues A_lo B_hi + A_hi B_lo + A_hi B_hi
-//            ("3xTF32", 24 instructions for 64 taus), PREC = 1 the hi product only.
-//   epilogue tcgen05.ld (lane = row: one thread owns a row, no shuffles); the accumulators are FP32, so the
-//            residual (y - R0 delta)/sigma + D is formed in FP32 from two-float constants; chi^2 summed in FP64.
+//            ("3xTF32", 24 instructions per column block for 64 taus), PREC = 1 the hi product only.  One extra K
+//            step (A from shared memory) adds the residual constants (y - R0 delta)/sigma, see kUmmaR0c below.
+//            The real and the imaginary columns are two blocks with their own mbarriers: the epilogue of the first
+//            runs under the MMAs of the second.
+//   epilogue tcgen05.ld (lane = row: one thread owns a row, no shuffles): the accumulators ARE the weighted
+//            residuals, chi^2 is their sum of squares (FP32 partial sums, combined in FP64).
 //
-// One elected lane of warp 0 issues the MMAs from the uniform datapath; tcgen05.commit arrives on an mbarrier.
-// Tensor memory per CTA: 128 accumulator columns + 128 operand columns = 256, so two CTAs share an SM's 512
-// (the stage-1 result aliases the accumulator columns, the b planes alias the A columns).  n_tau > 64 runs in
-// 64-tau chunks with separate stage-1 columns (512 columns, one CTA per SM; api.cu guarantees it).
+// One elected lane of warp 7 issues every MMA from the uniform datapath (tcgen05.commit only tracks the issuing
+// thread's instructions); completion arrives on mbarriers.  Tensor memory per CTA: 128 accumulator columns + 128
+// operand columns = 256, so two CTAs share an SM's 512 (the stage-1 result aliases the accumulator columns, the b
+// planes alias the A columns).  n_tau > 64 runs in 64-tau chunks with separate stage-1 columns (512 columns, one CTA
+// per SM; api.cu guarantees it); when the K planes exceed one CTA's shared memory a 2-CTA cluster splits the real |
+// imaginary columns and exchanges the partial chi^2 through distributed shared memory (cluster mode).
+// Polling the mbarriers from one warp per group (the others parked in a hardware barrier) was measured: no change.
 // The operand conventions (descriptor fields, A-in-TMEM layout) are pinned on hardware by tools/umma_probe.cu.
 // Restates reference Decomp_cyth (cython_funcs.pyx:75-94) + _log_likelihood (models.py:59-62) at TF32 precision.
 #pragma once
