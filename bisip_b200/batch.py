@@ -215,6 +215,21 @@ class BatchInversion:
              np.stack([relaxation_time_distribution(a[b, 1:], lt[b]) for b in range(a.shape[0])]))
         return m, m.sum(-1)
 
+    def get_autocorr_time(self, c=5, thin=1):
+        """Integrated autocorrelation time of every parameter of every spectrum, (B, ndim), from the kept chain of
+        the last ``fit(..., keep_chain=True)`` (emcee's estimator; ``thin`` = the thinning that fit used, so the
+        result is in steps).  Evaluated on the GPU in sub-batches."""
+        from .sampler import integrated_time_batch
+        if self.results is None or 'chain' not in self.results:
+            raise AssertionError('get_autocorr_time needs fit(..., keep_chain=True)')
+        ch = self.results['chain']
+        out = np.empty((ch.shape[0], ch.shape[-1]))
+        step = max(1, int(2 ** 27 // max(1, ch[0].size)))            # ~1 GB of float64 per sub-batch
+        for lo in range(0, ch.shape[0], step):
+            t = torch.from_numpy(ch[lo:lo + step]).to(self.device)
+            out[lo:lo + step] = integrated_time_batch(t, c=c, thin=thin).cpu().numpy()
+        return out
+
     def to_csv(self, path, ids=None):
         """One row per spectrum: id, acceptance, flags, mean/std/percentiles of every parameter."""
         from .products import batch_table

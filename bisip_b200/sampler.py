@@ -192,3 +192,23 @@ def integrated_time(x, c=5, tol=50, quiet=False):
                            "for {1} parameter(s). Use this estimate with caution and run a longer "
                            "chain!\nN/{0} = {2:.0f};\ntau: {3}".format(tol, int(np.sum(flag)), n_t / tol, tau_est))
     return tau_est
+
+
+def integrated_time_batch(chain, c=5, thin=1):
+    """``integrated_time`` for a batch of chains at once, on whatever device ``chain`` lives on:
+    chain (B, n_t, n_w, n_d) float64 tensor -> (B, n_d) tensor of integrated autocorrelation times (times ``thin``).
+    Same estimator as emcee.autocorr (walker-averaged normalised ACF through an FFT, Sokal's automatic window with
+    constant ``c``); used by ``BatchInversion.get_autocorr_time`` so that survey-scale batches get a convergence
+    diagnostic without a Python loop over spectra.  No ``tol`` check: callers compare ``n_t`` with the result."""
+    B, n_t, n_w, n_d = chain.shape
+    n = _next_pow_two(n_t)
+    x = chain - chain.mean(1, keepdim=True)
+    f = torch.fft.rfft(x, n=2 * n, dim=1)
+    acf = torch.fft.irfft(f * f.conj(), n=2 * n, dim=1)[:, :n_t]
+    acf = acf / acf[:, :1]
+    rho = acf.mean(2)                                              # (B, n_t, n_d)
+    taus = 2.0 * torch.cumsum(rho, 1) - 1.0
+    m = torch.arange(n_t, device=chain.device, dtype=chain.dtype)[None, :, None] < c * taus
+    first_false = torch.argmin(m.to(torch.int8), dim=1)            # emcee: argmin(m) if any(m) else n_t - 1
+    window = torch.where(m.any(1), first_false, torch.full_like(first_false, n_t - 1))
+    return thin * taus.gather(1, window[:, None, :])[:, 0]

@@ -60,3 +60,24 @@ def test_batch_rtd_and_table(tmp_path, gold_fl):
     cc = BatchInversion('colecole', w, gold_fl[f'{tag}/zn'], gold_fl[f'{tag}/zn_err'], nwalkers=32, nsteps=10)
     with pytest.raises(ValueError):
         cc.rtd()
+
+
+def test_batch_autocorr_time_on_the_kept_chain():
+    """Convergence diagnostic for batches: integrated autocorrelation times of every spectrum on
+    the GPU equal the per-chain emcee-style estimator, and the stretch move's tau is O(10) steps for 6 parameters."""
+    from bisip_b200 import sampler, synthetic, engine, _lib
+    from bisip_b200.batch import BatchInversion
+    _, w = synthetic.frequencies(64)
+    probe = BatchInversion('decomp', w, np.zeros((1, 2, 64)), np.ones((1, 2, 64)), poly_deg=4, n_tau=64)
+    fwd = lambda th, ww: engine.forward(probe._spec(), _lib.dev_f64(th[:, None, :], probe.device),
+                                        _lib.dev_f64(ww, probe.device))[:, 0].cpu().numpy()
+    syn = synthetic.make('decomp', 0, 6, fwd, N=64, poly_deg=4, n_tau=64)
+    inv = BatchInversion('decomp', w, syn['zn'], syn['zn_err'], nwalkers=64, nsteps=3000, poly_deg=4, n_tau=64, seed=9)
+    with pytest.raises(AssertionError):
+        inv.get_autocorr_time()
+    res = inv.fit(discard=1000, thin=2, keep_chain=True)
+    tau = inv.get_autocorr_time(thin=2)
+    assert tau.shape == (6, 6) and np.all(np.isfinite(tau))
+    for b in range(6):
+        np.testing.assert_allclose(tau[b], 2 * sampler.integrated_time(res['chain'][b], quiet=True), rtol=1e-9)
+    assert 5 < np.median(tau) < 200

@@ -185,6 +185,23 @@ def test_walkers_independent_and_autocorr():
     assert abs(tau[0] - 9.0) < 1.0
 
 
+def test_batched_autocorr_time_matches_the_per_chain_estimator():
+    import torch
+    from bisip_b200 import sampler
+    rng = np.random.default_rng(3)
+    B, T, W, D = 3, 600, 8, 2
+    x = np.zeros((B, T, W, D))
+    for b, phi in enumerate((0.5, 0.8, 0.95)):                       # AR(1) chains: tau = (1 + phi)/(1 - phi)
+        e = rng.standard_normal((T, W, D))
+        for t in range(1, T):
+            x[b, t] = phi * x[b, t - 1] + e[t]
+    got = sampler.integrated_time_batch(torch.from_numpy(x), c=5, thin=2).numpy()
+    for b in range(B):
+        ref = 2 * sampler.integrated_time(x[b], c=5, quiet=True)
+        np.testing.assert_allclose(got[b], ref, rtol=1e-10)
+    assert got[2].mean() > got[1].mean() > got[0].mean()
+
+
 def test_synthetic_generator_is_shard_independent():
     from bisip_b200 import synthetic
     fwd = lambda th, w: np.stack([np.stack([np.outer(t[:1], np.ones_like(w))[0], -0.1 * t[1] * np.ones_like(w)]) for t in th])
