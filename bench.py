@@ -370,7 +370,8 @@ def run_gpu(args):
                          "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_step,
                          "algorithmic_flop_per_eval": FLOP_PER_EVAL},
             "cpu_baseline": {"value": cpu_v, "unit": "evals/s", "cores": min(cores, B), "kind": "reference", "sample": cpu_sample,
-                             "wall_s": cpu_wall,
+                             "wall_s": cpu_wall, "evals_per_s_per_core": cpu_v / min(cores, B),
+                             "extrapolated_days_for_full_config_on_these_cores": 1e5 * WALKERS * NSTEPS / cpu_v / 86400.0,
                              "note": "reference models.py + Cython (oracle/_ref) under oracle/emcee_restatement.py"},
             "clocks": clk, "acceptance_fraction": acc, "nan_flags": flags_bad,
             "variants": {"note": "reduced-precision decomposition kernels on a slice of the same shard (ensemble kernel alone); "
