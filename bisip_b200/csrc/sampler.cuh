@@ -624,7 +624,9 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
           const u32x4 r = philox4x32_10((uint32_t)q, t, spec, (uint32_t)(2 + 2 * sp), k0, k1);
           const double u2 = u53(r.x, r.y);
           s.u2[q] = u2;
-          s.lf[q] = (double)((float)(ndim - 1) * logf((float)zzb[q]) - logf((float)u2));
+          // MUFU.LG2-based logarithms: |error| <= ~4e-6 here (zz in [1/a, a]; |ln u| <= 37 at 2^-22 relative), far
+          // inside the 2^-12 margin below which accept_filter() hands the decision to the FP64 logarithms
+          s.lf[q] = (double)((float)(ndim - 1) * __logf((float)zzb[q]) - __logf((float)u2));
         }
       }
       FINE_MARK(6)
