@@ -17,7 +17,8 @@ mean / std summary, and for N>1 the NCCL all-gather of the summaries.
 `roofline`: ensemble_decomp kernel (the dominant launch): algorithmic flops (17,792 per eval,
            SURVEY.md §8d) / its CUDA-event duration, against the FP64 DMMA peak measured on this
            box by tools/peaks (MEASURED_PEAKS.json has no FP64 figure).
-`variants`: the TF32 / 3xTF32 tcgen05 kernels on a slice of the same shard (kernel alone), next to the FP64 numbers.
+`variants`: the collapsed FP64 kernel (precision='fp64-collapsed') and the TF32 / 3xTF32 tcgen05 kernels on the same
+           shard (kernel alone on a slice, and the whole shard end to end), next to the default FP64 DMMA numbers.
 `cpu_baseline`: the reference's own Cython + NumPy log-probability (oracle/_ref) under the emcee
            restatement, on all host cores, on a bounded sample of the same spectra.
 `--impl reference`: that CPU arm alone, as its own JSON line.
@@ -300,8 +301,8 @@ def run_gpu(args):
     #      Reported next to the FP64 numbers; `value`, `e2e` and `roofline` stay FP64.
     variants = {}
     if rank == 0:
-        nv = min(B, 592)
-        for prec in ("3xtf32", "tf32"):
+        for prec in ("fp64-collapsed", "3xtf32", "tf32"):
+            nv = min(B, 2368 if prec == "fp64-collapsed" else 592)       # one full wave of resident CTAs
             alt = BatchInversion('decomp', syn['w'], zn_h[:nv], ze_h[:nv], nwalkers=WALKERS, nsteps=NSTEPS, poly_deg=POLY_DEG,
                                  n_tau=N_TAU, seed=SEED, spectrum_offset=b0, device=dev, precision=prec)
             aspec = alt._spec()
@@ -320,19 +321,26 @@ def run_gpu(args):
                               "acceptance_fraction": float(r_alt['accepted'].double().mean().item() / 500),
                               "nan_flags": int((r_alt['flags'] != 0).sum().item())}
             del r_alt
-        # the whole shard end to end in 3xTF32 through the public API (pinned host inputs, host summaries), like `e2e`
-        alt = BatchInversion('decomp', syn['w'], zn_h, ze_h, nwalkers=WALKERS, nsteps=NSTEPS, poly_deg=POLY_DEG,
-                             n_tau=N_TAU, seed=SEED, spectrum_offset=b0, device=dev, precision='3xtf32')
-        best = 1e30
-        for rep in range(2):
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            r_alt = alt.fit(p0=p0_h, discard=DISCARD, thin=THIN, percentiles=PCT)
-            torch.cuda.synchronize()
-            best = min(best, time.perf_counter() - t0)
-        variants['3xtf32'].update({"e2e_evals_per_s": B * WALKERS * NSTEPS / best, "e2e_spectra_per_s": B / best,
+        # the whole shard end to end through the public API (pinned host inputs, host summaries), like `e2e`
+        for prec in ("fp64-collapsed", "3xtf32"):
+            alt = BatchInversion('decomp', syn['w'], zn_h, ze_h, nwalkers=WALKERS, nsteps=NSTEPS, poly_deg=POLY_DEG,
+                                 n_tau=N_TAU, seed=SEED, spectrum_offset=b0, device=dev, precision=prec)
+            best = 1e30
+            for rep in range(2):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                r_alt = alt.fit(p0=p0_h, discard=DISCARD, thin=THIN, percentiles=PCT)
+                torch.cuda.synchronize()
+                best = min(best, time.perf_counter() - t0)
+            variants[prec].update({"e2e_evals_per_s": B * WALKERS * NSTEPS / best, "e2e_spectra_per_s": B / best,
                                    "e2e_ms_per_step": 1e3 * best, "e2e_nan_flags": int((r_alt['flags'] != 0).sum())})
-        del r_alt, alt
+            if prec == "fp64-collapsed":
+                # FP64 to rounding: the sampler takes the same decisions as the two-stage DMMA path (`r` = last e2e result)
+                variants[prec]["summaries_identical_to_fp64"] = bool(
+                    np.array_equal(r_alt['percentiles'], r['percentiles'])
+                    and np.array_equal(r_alt['acceptance_fraction'], r['acceptance_fraction']))
+                variants[prec]["algorithmic_flop_per_eval"] = 2 * 2 * N_FREQ * (POLY_DEG + 1 + 2)
+            del r_alt, alt
     if rank == 0:
         k_ms = float(np.mean(kern_ms))
         flops_launch = FLOP_PER_EVAL * float(B) * WALKERS * (NSTEPS + 1)       # +1: log-prob of p0
@@ -374,8 +382,10 @@ def run_gpu(args):
                              "extrapolated_days_for_full_config_on_these_cores": 1e5 * WALKERS * NSTEPS / cpu_v / 86400.0,
                              "note": "reference models.py + Cython (oracle/_ref) under oracle/emcee_restatement.py"},
             "clocks": clk, "acceptance_fraction": acc, "nan_flags": flags_bad,
-            "variants": {"note": "reduced-precision decomposition kernels on a slice of the same shard (ensemble kernel alone); "
-                                 "tolerances in profiles/r01f_tf32_study.md; value / e2e / roofline above are FP64",
+            "variants": {"note": "other decomposition kernels on the same shard: evals_per_s = ensemble kernel alone on a slice (CUDA "
+                                 "events), e2e_* = the whole shard through BatchInversion.fit like `e2e`.  fp64-collapsed is FP64 "
+                                 "(same 1e-12 parity, z = (L K) a); tf32 / 3xtf32 tolerances in profiles/r01f_tf32_study.md.  "
+                                 "value / e2e / roofline above are the default two-stage FP64 DMMA path",
                          "fp64_evals_per_s_kernel": evals_step / world * (NSTEPS + 1) / NSTEPS / (k_ms * 1e-3), **variants},
         }
         print(json.dumps(line))

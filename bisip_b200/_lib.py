@@ -14,16 +14,16 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BISIP_B200_LIB", os.path.join(_HERE, "csrc", "libbisip_b200.so"))   # env: developer builds
 
 MODEL_COLECOLE, MODEL_DIAS, MODEL_SHIN, MODEL_DECOMP = 0, 1, 2, 3
-PREC_FP64, PREC_TF32, PREC_3XTF32, PREC_TF32_MMA, PREC_3XTF32_MMA = 0, 1, 2, 3, 4
+PREC_FP64, PREC_TF32, PREC_3XTF32, PREC_TF32_MMA, PREC_3XTF32_MMA, PREC_FP64_COLLAPSED = 0, 1, 2, 3, 4, 5
 PRECISIONS = {"fp64": PREC_FP64, "tf32": PREC_TF32, "3xtf32": PREC_3XTF32,
-              "tf32-mma": PREC_TF32_MMA, "3xtf32-mma": PREC_3XTF32_MMA}
+              "tf32-mma": PREC_TF32_MMA, "3xtf32-mma": PREC_3XTF32_MMA, "fp64-collapsed": PREC_FP64_COLLAPSED}
 MAX_PCT = 16
 
 EXPORTS = ("bisip_abi_version", "bisip_last_error", "bisip_launch_count", "bisip_forward",
            "bisip_log_probability", "bisip_decomp_build_kernel", "bisip_n_keep",
            "bisip_ensemble_run", "bisip_column_stats_workspace", "bisip_column_stats",
            "bisip_decomp_kernel_kind")
-KERNEL_KINDS = {0: "dmma", 1: "dmma-cluster", 2: "mma-tf32", 3: "tcgen05", 4: "tcgen05-cluster"}
+KERNEL_KINDS = {0: "dmma", 1: "dmma-cluster", 2: "mma-tf32", 3: "tcgen05", 4: "tcgen05-cluster", 5: "fp64-collapsed"}
 
 
 class BisipError(RuntimeError):

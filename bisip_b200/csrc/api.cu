@@ -50,7 +50,7 @@ int check_desc(const bisip_model_desc* d) {
       if (d->n_tau <= 0 || d->n_coef <= 0) return fail(BISIP_ERR_BAD_ARG, "Decomp n_tau/n_coef must be positive");
       if (d->ndim != 1 + d->n_coef) return fail(BISIP_ERR_BAD_ARG, "Decomp ndim != 1+n_coef");
       if (d->n_coef > 8) return fail(BISIP_ERR_UNSUPPORTED, "Decomp poly_deg > 7 not supported");
-      if (d->precision < BISIP_PREC_FP64 || d->precision > BISIP_PREC_3XTF32_MMA)
+      if (d->precision < BISIP_PREC_FP64 || d->precision > BISIP_PREC_FP64_COLLAPSED)
         return fail(BISIP_ERR_BAD_ARG, "unknown precision");
       break;
     default:
@@ -82,6 +82,11 @@ constexpr int kMinBVec = BISIP_VEC_MINB;
 constexpr int kMinBVec = 4;      // 256-thread CTAs, 64 registers
 #endif
 constexpr int kVecSmallW = 128;  // walkers up to which the 128-thread variant is used
+#ifdef BISIP_COLLAPSED_MINB
+constexpr int kMinBCollapsed = BISIP_COLLAPSED_MINB;
+#else
+constexpr int kMinBCollapsed = 4;   // collapsed decomposition, 256-thread CTAs (64 registers)
+#endif
 
 // launch ensemble_kernel<VecEvaluator<Row>> in the shape picked for W walkers; MB128 = CTAs/SM of the
 // 128-thread variant (8 -> 64 registers, 6 -> 80 registers)
@@ -123,6 +128,40 @@ __global__ void __launch_bounds__(kThreads) decomp_batch_kernel(const BatchParam
     } else {
       NoSide ns;
       decomp_eval_chi<KC>(s, sh, prop, ndim, n, kRows, chi, ns);
+      __syncthreads();
+      for (int q = threadIdx.x; q < n; q += kThreads)
+        P.lp[(size_t)b * P.n_theta + r0 + q] =
+            in_bounds(prop + q * ndim, bnd, ndim) ? -0.5 * (chi[q] + s.llconst) : neg_inf();
+    }
+    __syncthreads();
+  }
+}
+
+// Collapsed decomposition (decomp_collapsed.cuh): same grid as decomp_batch_kernel.
+template <bool WANT_Z>
+__global__ void __launch_bounds__(kThreads) decomp_c_batch_kernel(const BatchParams P) {
+  extern __shared__ __align__(16) double smem[];
+  const int b = blockIdx.y, ndim = P.d.ndim, N = P.d.n_freq;
+  DecompCShape sh(P.d.n_freq, P.d.n_tau, P.d.n_coef);
+  DecompCSmem s;
+  double* p = decomp_c_carve(s, smem, sh, kRows);
+  double* prop = p; p += kRows * ndim;
+  double* chi = p; p += kRows;
+  double* bnd = p; p += 2 * ndim;
+  double* red = p;
+  if (!WANT_Z) for (int i = threadIdx.x; i < 2 * ndim; i += kThreads) bnd[i] = P.bounds[i];
+  decomp_c_init(s, sh, P.d.c_exp, P.w + (size_t)b * P.w_stride, P.taus + (size_t)b * P.tau_stride,
+                P.log_taus + (size_t)b * P.tau_stride * P.d.n_coef,
+                WANT_Z ? nullptr : P.y + (size_t)b * 2 * N, WANT_Z ? nullptr : P.yerr + (size_t)b * 2 * N, red);
+  for (int r0 = blockIdx.x * kRows; r0 < P.n_theta; r0 += gridDim.x * kRows) {
+    const int n = min(kRows, P.n_theta - r0);
+    const double* th = P.theta + ((size_t)b * P.n_theta + r0) * ndim;
+    for (int i = threadIdx.x; i < kRows * ndim; i += kThreads) prop[i] = (i < n * ndim) ? th[i] : 0.0;
+    __syncthreads();
+    if (WANT_Z) {
+      decomp_c_eval_Z(s, sh, prop, ndim, n, P.Z + ((size_t)b * P.n_theta + r0) * 2 * N);
+    } else {
+      decomp_c_eval_chi(s, sh, prop, ndim, n, kRows, chi);
       __syncthreads();
       for (int q = threadIdx.x; q < n; q += kThreads)
         P.lp[(size_t)b * P.n_theta + r0 + q] =
@@ -266,7 +305,8 @@ int plan_rc(const bisip_model_desc& d, size_t other_bytes, int rows_pad, RcPlan*
 }
 // the clustered ("rc") layout serves every mma.sync reduced-precision run and every FP64 run with n_tau > 64
 bool use_rc(const bisip_model_desc& d) {
-  return d.model == BISIP_MODEL_DECOMP && (d.n_tau > 64 || d.precision != BISIP_PREC_FP64);
+  return d.model == BISIP_MODEL_DECOMP && d.precision != BISIP_PREC_FP64_COLLAPSED &&
+         (d.n_tau > 64 || d.precision != BISIP_PREC_FP64);
 }
 
 // tcgen05 path (decomp_umma.cuh): BISIP_PREC_TF32 / _3XTF32 whenever one M = 128 tile holds a half-step
@@ -413,6 +453,14 @@ int run_batch(const BatchParams& P, cudaStream_t st) {
       return launch(decomp_umma_batch_kernel<1, WANT_Z>, g, up.smem, st, "decomp_umma_tf32_batch", &P);
     }
   }
+  if (P.d.model == BISIP_MODEL_DECOMP && P.d.precision == BISIP_PREC_FP64_COLLAPSED) {
+    const size_t smem = (((size_t)kRows * P.d.ndim + kRows + 2 * P.d.ndim + kWarps) +
+                         decomp_c_smem_doubles(DecompCShape(P.d.n_freq, P.d.n_tau, P.d.n_coef), kRows)) * 8;
+    int chunks = ceil_div(P.n_theta, kRows);
+    const int cap = max(1, (148 * 4) / max(1, P.B));
+    if (chunks > cap) chunks = cap;
+    return launch(decomp_c_batch_kernel<WANT_Z>, dim3(chunks, P.B), smem, st, "decomp_collapsed_batch", &P);
+  }
   if (use_rc(P.d)) {
     RcPlan plan;
     const size_t other = ((size_t)kRows * P.d.ndim + kRows + 2 * P.d.ndim + kWarps) * 8;
@@ -479,6 +527,7 @@ int bisip_decomp_kernel_kind(const bisip_model_desc* desc, int n_walkers) {
   if (int rc = check_desc(desc)) return rc;
   if (desc->model != BISIP_MODEL_DECOMP || n_walkers < 2) return fail(BISIP_ERR_BAD_ARG, "bisip_decomp_kernel_kind: bad argument");
   const size_t other = sampler_smem_bytes(n_walkers, desc->ndim);
+  if (desc->precision == BISIP_PREC_FP64_COLLAPSED) return BISIP_KERNEL_FP64_COLLAPSED;
   {
     const UmmaPlan up = plan_umma(*desc, other, (n_walkers + 1) / 2, true);
     if (up.ok) return up.cluster ? BISIP_KERNEL_TCGEN05_CLUSTER : BISIP_KERNEL_TCGEN05;
@@ -580,6 +629,13 @@ int bisip_ensemble_run(const bisip_model_desc* desc, int n_spectra, int n_walker
       smem += VecEvaluator<ShinRow>::smem_doubles(*desc, rp) * 8;
       return launch_vec_ensemble<ShinRow, 6>(P, grid, smem, st, "ensemble_shin");
     default: {
+      if (desc->precision == BISIP_PREC_FP64_COLLAPSED) {
+        smem += DecompCollapsedEvaluator::smem_doubles(*desc, rp) * 8;
+        if (n_walkers <= kVecSmallW)
+          return launch(ensemble_kernel<DecompCollapsedEvaluator, 8, 128>, grid, smem, st, "ensemble_decomp_collapsed", &P, 128);
+        return launch(ensemble_kernel<DecompCollapsedEvaluator, kMinBCollapsed, kThreads>, grid, smem, st,
+                      "ensemble_decomp_collapsed", &P, kThreads);
+      }
       {
         const UmmaPlan up = plan_umma(*desc, smem, (n_walkers + 1) / 2, true);
         if (up.ok && up.cluster) {

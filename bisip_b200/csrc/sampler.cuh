@@ -16,6 +16,7 @@
 #include "decomp_rc.cuh"
 #include "decomp_tf32.cuh"
 #include "decomp_umma.cuh"
+#include "decomp_collapsed.cuh"
 #include "models.cuh"
 
 namespace bisip {
@@ -350,6 +351,7 @@ struct DecompEvaluator {
     decomp_init(sm, sh, d.c_exp, w, taus, log_taus, y, yerr, red);
   }
   __device__ double llconst() const { return sm.llconst; }
+  __device__ __forceinline__ double chi_of(const double* chi, int q) const { return chi[q]; }
   __device__ int iters_per_warp(int nrows) const { return decomp_iters_per_warp(sh, nrows); }
   __device__ void eval_chi(const double* prop, int ndim, int nrows, double* chi, RankSide& side) {
     decomp_eval_chi<KC>(sm, sh, prop, ndim, nrows, rows_pad, chi, side);
@@ -375,6 +377,7 @@ struct DecompRCEvaluator {
     decomp_rc_init(sm, sh, d.c_exp, w, taus, log_taus, y, yerr, red);
   }
   __device__ double llconst() const { return sm.llconst; }
+  __device__ __forceinline__ double chi_of(const double* chi, int q) const { return chi[q]; }
   __device__ int iters_per_warp(int) const { return 0; }
   __device__ void eval_chi(const double* prop, int ndim, int nrows, double* chi, RankSide& side) {
     side.finish();
@@ -402,6 +405,7 @@ struct DecompTF32Evaluator {
     decomp_tf32_init<PREC>(sm, sh, d.c_exp, w, taus, log_taus, y, yerr, red);
   }
   __device__ double llconst() const { return sm.llconst; }
+  __device__ __forceinline__ double chi_of(const double* chi, int q) const { return chi[q]; }
   __device__ int iters_per_warp(int) const { return 0; }
   __device__ void eval_chi(const double* prop, int ndim, int nrows, double* chi, RankSide& side) {
     side.finish();
@@ -428,12 +432,46 @@ struct DecompUmmaEvaluator {
     decomp_umma_init<PREC>(sm, sh, d.c_exp, w, taus, log_taus, y, yerr, red);
   }
   __device__ double llconst() const { return sm.llconst; }
+  __device__ __forceinline__ double chi_of(const double* chi, int q) const { return chi[q]; }
   __device__ int iters_per_warp(int) const { return 0; }
   __device__ void eval_chi(const double* prop, int ndim, int nrows, double* chi, RankSide& side) {
     side.finish();
     decomp_umma_eval<PREC, false>(sm, sh, prop, ndim, nrows, chi, nullptr);
   }
   __device__ void release() { decomp_umma_release(sm, sh); }   // frees the tensor memory
+};
+
+// Collapsed form z = (L K) a on the FP64 vector pipe (decomp_collapsed.cuh): precision 'fp64-collapsed'.
+struct DecompCollapsedEvaluator {
+  static constexpr bool kClustered = false;
+  static constexpr bool kNeedsPrepare = false;
+  __device__ __forceinline__ void prepare_row(int, const double*) {}
+  __device__ __forceinline__ void release() {}
+  DecompCSmem sm;
+  DecompCShape sh;
+  int rows_pad, ngroups;
+  __device__ DecompCollapsedEvaluator(const bisip_model_desc& d, int, int) : sh(d.n_freq, d.n_tau, d.n_coef) {}
+  static __host__ size_t smem_doubles(const bisip_model_desc& d, int rows_pad) {
+    return decomp_c_smem_doubles(DecompCShape(d.n_freq, d.n_tau, d.n_coef), rows_pad);
+  }
+  __device__ double* carve(double* base, int rp) { rows_pad = rp; return decomp_c_carve(sm, base, sh, rp); }
+  __device__ void init(const bisip_model_desc& d, const double* w, const double* taus, const double* log_taus,
+                       const double* y, const double* yerr, double* red) {
+    decomp_c_init(sm, sh, d.c_exp, w, taus, log_taus, y, yerr, red);
+  }
+  __device__ double llconst() const { return sm.llconst; }
+  // the per-column-group partial sums are added here, in group order, by the thread that takes the accept
+  // decision: no reduction pass and no extra barrier inside the evaluation
+  __device__ __forceinline__ double chi_of(const double*, int q) const {
+    double acc = 0.0;
+    for (int g = 0; g < ngroups; ++g) acc += sm.part[(size_t)g * rows_pad + q];
+    return acc;
+  }
+  __device__ int iters_per_warp(int) const { return 0; }
+  __device__ void eval_chi(const double* prop, int ndim, int nrows, double* chi, RankSide& side) {
+    side.finish();
+    ngroups = decomp_c_eval_parts(sm, sh, prop, ndim, nrows, rows_pad);
+  }
 };
 
 template <class Row>
@@ -452,6 +490,7 @@ struct VecEvaluator {
     vec_init(sm, N, w, y, yerr, red);
   }
   __device__ double llconst() const { return sm.llconst; }
+  __device__ __forceinline__ double chi_of(const double* chi, int q) const { return chi[q]; }
   __device__ int iters_per_warp(int) const { return 0; }
   // theta-only constants of proposal q (exp / sincospi / divisions), by the thread that built it
   __device__ __forceinline__ void prepare_row(int q, const double* th) {
@@ -547,7 +586,7 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
     ev.eval_chi(s.prop, ndim, n, s.chi, side);
     __syncthreads();
     for (int q = tid; q < n; q += NT) {
-      const double v = in_bounds(s.prop + q * ndim, s.bnd, ndim) ? -0.5 * (s.chi[q] + llc) : neg_inf();
+      const double v = in_bounds(s.prop + q * ndim, s.bnd, ndim) ? -0.5 * (ev.chi_of(s.chi, q) + llc) : neg_inf();
       if (v != v) flag |= 2;
       s.lp[off + q] = v;
     }
@@ -646,7 +685,7 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
           const int q = idx;
           const int k = list[off + q];
           const double lpo = s.lp[k];
-          const double lpn = s.inb[q] ? -0.5 * (s.chi[q] + llc) : neg_inf();
+          const double lpn = s.inb[q] ? -0.5 * (ev.chi_of(s.chi, q) + llc) : neg_inf();
           if (lpn != lpn) flag |= 1;
           // emcee: accept iff (ndim-1) ln zz + lp' - lp > ln u.  The logarithms were taken in FP32
           // (|error| < 1e-5): unless the margin is below the threshold the FP64 decision is already

@@ -191,7 +191,9 @@ class PolynomialDecomposition(Inversion):
         poly_deg (int): polynomial degree of the relaxation-time distribution. Defaults to 5.
         c_exp (float): 1.0 -> Debye, 0.5 -> Warburg. Defaults to 1.0.
         n_tau (int, optional): number of relaxation times; the reference hard-codes ``2*N``.
-        precision (str): 'fp64' (DMMA), 'tf32' or '3xtf32'.
+        precision (str): 'fp64' (two-stage contraction on DMMA tiles, the default), 'fp64-collapsed'
+            (FP64, z = (L K) a with L K built once per spectrum: same 1e-12 parity, ~10x fewer flops),
+            'tf32' or '3xtf32' (tcgen05 tensor cores, stated tolerance).
     """
 
     _model_id = _lib.MODEL_DECOMP

@@ -57,7 +57,11 @@ enum bisip_precision {
                            (<= 256 walkers, n_freq <= 64, K planes fit in shared memory), mma.sync tiles otherwise */
   BISIP_PREC_3XTF32 = 2,     /* error-compensated 3xTF32 split, same dispatch */
   BISIP_PREC_TF32_MMA = 3,   /* TF32, always the mma.sync tile kernel (kept for the comparison study) */
-  BISIP_PREC_3XTF32_MMA = 4  /* 3xTF32, always the mma.sync tile kernel */
+  BISIP_PREC_3XTF32_MMA = 4, /* 3xTF32, always the mma.sync tile kernel */
+  BISIP_PREC_FP64_COLLAPSED = 5 /* FP64, decomposition re-associated to z = (L K) a: the theta-independent product
+                                   G = L K ((poly_deg+1) x 2N) is built once per spectrum (compensated sums), one
+                                   evaluation is 2N (poly_deg+3) FMAs on the FP64 vector pipe.  Same 1e-12 parity bar as
+                                   BISIP_PREC_FP64, ~10x fewer flops; the two-stage DMMA contraction stays the default */
 };
 
 enum bisip_status {
@@ -93,7 +97,8 @@ enum bisip_kernel_kind {
   BISIP_KERNEL_DMMA_CLUSTER = 1, /* FP64 DMMA, stage-1 recompute, columns split over a CTA cluster (n_tau > 64) */
   BISIP_KERNEL_MMA_TF32 = 2,     /* TF32 / 3xTF32 mma.sync tiles */
   BISIP_KERNEL_TCGEN05 = 3,      /* TF32 / 3xTF32 tcgen05.mma, operands and accumulators in tensor memory */
-  BISIP_KERNEL_TCGEN05_CLUSTER = 4 /* the same with the real | imaginary columns split over a 2-CTA cluster */
+  BISIP_KERNEL_TCGEN05_CLUSTER = 4, /* the same with the real | imaginary columns split over a 2-CTA cluster */
+  BISIP_KERNEL_FP64_COLLAPSED = 5   /* collapsed form on the FP64 vector pipe (BISIP_PREC_FP64_COLLAPSED, any n_tau) */
 };
 int bisip_decomp_kernel_kind(const bisip_model_desc *desc, int n_walkers);
 

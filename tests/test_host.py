@@ -162,10 +162,12 @@ def test_header_enums_match_python_constants():
     assert (val['BISIP_MODEL_COLECOLE'], val['BISIP_MODEL_DIAS'], val['BISIP_MODEL_SHIN'], val['BISIP_MODEL_DECOMP']) == \
         (_lib.MODEL_COLECOLE, _lib.MODEL_DIAS, _lib.MODEL_SHIN, _lib.MODEL_DECOMP)
     assert _lib.PRECISIONS == {'fp64': val['BISIP_PREC_FP64'], 'tf32': val['BISIP_PREC_TF32'], '3xtf32': val['BISIP_PREC_3XTF32'],
-                               'tf32-mma': val['BISIP_PREC_TF32_MMA'], '3xtf32-mma': val['BISIP_PREC_3XTF32_MMA']}
+                               'tf32-mma': val['BISIP_PREC_TF32_MMA'], '3xtf32-mma': val['BISIP_PREC_3XTF32_MMA'],
+                               'fp64-collapsed': val['BISIP_PREC_FP64_COLLAPSED']}
     assert _lib.KERNEL_KINDS == {val['BISIP_KERNEL_DMMA']: 'dmma', val['BISIP_KERNEL_DMMA_CLUSTER']: 'dmma-cluster',
                                  val['BISIP_KERNEL_MMA_TF32']: 'mma-tf32', val['BISIP_KERNEL_TCGEN05']: 'tcgen05',
-                                 val['BISIP_KERNEL_TCGEN05_CLUSTER']: 'tcgen05-cluster'}
+                                 val['BISIP_KERNEL_TCGEN05_CLUSTER']: 'tcgen05-cluster',
+                                 val['BISIP_KERNEL_FP64_COLLAPSED']: 'fp64-collapsed'}
 
 
 def test_walkers_independent_and_autocorr():
