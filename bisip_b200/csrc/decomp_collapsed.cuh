@@ -9,7 +9,7 @@
 // log-probability meet the same 1e-12 parity bar against the reference (tests/test_gpu_parity.py).
 // With D <= 8 the contraction is too thin for tensor tiles (an m16n8k8 DMMA tile pads D to 8 and runs
 // on the same pipe at the same flop rate as DFMA), so it runs on the FP64 vector pipe: a thread owns
-// one proposal and one group of columns; the column records are warp-uniform broadcast loads.
+// kCRows proposals and one group of columns; the column records are warp-uniform broadcast loads.
 //
 // north_star grades the two-stage contraction on DMMA tiles, which therefore stays the default
 // (decomp_eval.cuh); this evaluator is the opt-in fast path for users who only want the answer.
@@ -114,20 +114,33 @@ __device__ inline void decomp_c_init(DecompCSmem& s, const DecompCShape& sh, dou
 #endif
 constexpr int kCRows = BISIP_COLLAPSED_RPT;
 
-// Work split of one evaluation: thread-rows (RPT proposals each) padded to whole warps (so that the column group is
-// warp-uniform), the real block and the imaginary block each cut into `gh` column groups of `cpg` columns.
-struct DecompCSplit {
-  int trows, rows_p, gh, cpg, ngroups;
-  __device__ __forceinline__ DecompCSplit(int nrows, int N, int rpt) {
-    const int NT = blockDim.x;
-    trows = ceil_div(nrows, rpt);
-    rows_p = (trows + 31) & ~31;
+// Work split of an evaluation, fixed once per CTA for the largest number of rows it will see (`rows_cap`; integer
+// divisions are ~40 instructions each and used to be 8 % of the kernel when this was redone per evaluation):
+// thread-rows (rpt proposals each) padded to whole warps so that a warp works on ONE column group, the real block and
+// the imaginary block each cut into `gh` column groups of `cpg` columns.  Thread t owns thread-rows tr0, tr0+tstep, ...
+// and groups g0, g0+gstep, ...; an evaluation of fewer rows leaves the threads of the missing rows idle.
+struct DecompCPlan {
+  int rpt, trows, gh, cpg, ngroups, tr0, tstep, g0, gstep;
+  __device__ __forceinline__ void make(int rows_cap, int N) {
+    const int NT = blockDim.x, tid = threadIdx.x;
+    rpt = (kCRows > 1 && rows_cap >= 32 * kCRows) ? kCRows : 1;
+    trows = ceil_div(rows_cap, rpt);
+    const int rows_p = (trows + 31) & ~31;
     gh = NT / (2 * rows_p);
     if (gh < 1) gh = 1;
     if (gh > N) gh = N;
     cpg = ceil_div(N, gh);
     gh = ceil_div(N, cpg);
     ngroups = 2 * gh;       // <= NT/32 <= kWarps
+    if (rows_p <= NT) {     // NT/rows_p >= ngroups groups side by side: one pass
+      gstep = NT / rows_p;
+      g0 = tid / rows_p;
+      tr0 = tid - g0 * rows_p;
+      tstep = rows_p;
+      if (g0 >= gstep) g0 = ngroups;   // leftover threads
+    } else {                // more thread-rows than threads: every thread walks all groups
+      gstep = 1; g0 = 0; tr0 = tid; tstep = NT;
+    }
   }
 };
 
@@ -155,69 +168,67 @@ __device__ __forceinline__ void decomp_c_rows(const double* __restrict__ rec, in
   }
 }
 
-// Partial chi^2 of every (proposal, column group) into s.part[group][row]; returns the number of groups.  No barrier.
+// Partial chi^2 of every (proposal, column group) into s.part[group][row].  No barrier.
 template <int D, int RPT>
-__device__ __forceinline__ int decomp_c_parts_dr(const DecompCSmem& s, const DecompCShape& sh,
-                                                 const double* __restrict__ prop, int ndim, int nrows, int rows_pad) {
-  const int NT = blockDim.x;
-  const DecompCSplit sp(nrows, sh.N, RPT);
-  for (int item = threadIdx.x; item < sp.rows_p * sp.ngroups; item += NT) {
-    const int grp = item / sp.rows_p, tr = item - grp * sp.rows_p;      // grp is warp-uniform
-    if (tr >= sp.trows) continue;
-    const int blk = grp >= sp.gh ? 1 : 0, gi = grp - blk * sp.gh;
-    const int c0 = blk * sh.N + gi * sp.cpg, c1 = blk * sh.N + min(sh.N, (gi + 1) * sp.cpg);
+__device__ __forceinline__ void decomp_c_parts_dr(const DecompCSmem& s, const DecompCShape& sh, const DecompCPlan& pl,
+                                                  const double* __restrict__ prop, int ndim, int nrows, int rows_pad) {
+  for (int tr = pl.tr0; tr < pl.trows; tr += pl.tstep) {
+    if (tr >= nrows) break;
     double R0[RPT], ra[RPT][D], x[RPT];
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
-      const int row = tr + r * sp.trows;
+      const int row = tr + r * pl.trows;
       const double* th = prop + (size_t)(row < nrows ? row : tr) * ndim;
       R0[r] = th[0];
 #pragma unroll
       for (int i = 0; i < D; ++i) ra[r][i] = R0[r] * th[1 + i];
     }
-    if (blk) decomp_c_rows<D, RPT, false>(s.rec, c0, c1, R0, ra, x);
-    else decomp_c_rows<D, RPT, true>(s.rec, c0, c1, R0, ra, x);
+    for (int grp = pl.g0; grp < pl.ngroups; grp += pl.gstep) {      // grp is warp-uniform
+      const int blk = grp >= pl.gh ? 1 : 0, gi = grp - blk * pl.gh;
+      const int c0 = blk * sh.N + gi * pl.cpg, c1 = blk * sh.N + min(sh.N, (gi + 1) * pl.cpg);
+      if (blk) decomp_c_rows<D, RPT, false>(s.rec, c0, c1, R0, ra, x);
+      else decomp_c_rows<D, RPT, true>(s.rec, c0, c1, R0, ra, x);
 #pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-      const int row = tr + r * sp.trows;
-      if (row < nrows) s.part[(size_t)grp * rows_pad + row] = x[r];
+      for (int r = 0; r < RPT; ++r) {
+        const int row = tr + r * pl.trows;
+        if (row < nrows) s.part[(size_t)grp * rows_pad + row] = x[r];
+      }
     }
   }
-  return sp.ngroups;
 }
 
 template <int D>
-__device__ __forceinline__ int decomp_c_parts_d(const DecompCSmem& s, const DecompCShape& sh,
-                                                const double* __restrict__ prop, int ndim, int nrows, int rows_pad) {
-  if (kCRows > 1 && nrows >= 32 * kCRows) return decomp_c_parts_dr<D, kCRows>(s, sh, prop, ndim, nrows, rows_pad);
-  return decomp_c_parts_dr<D, 1>(s, sh, prop, ndim, nrows, rows_pad);
+__device__ __forceinline__ void decomp_c_parts_d(const DecompCSmem& s, const DecompCShape& sh, const DecompCPlan& pl,
+                                                 const double* __restrict__ prop, int ndim, int nrows, int rows_pad) {
+  if (kCRows > 1 && pl.rpt == kCRows) decomp_c_parts_dr<D, kCRows>(s, sh, pl, prop, ndim, nrows, rows_pad);
+  else decomp_c_parts_dr<D, 1>(s, sh, pl, prop, ndim, nrows, rows_pad);
 }
 
-// s.part[group][row] = sum over the group's columns of ((y_c - Z_c)/sigma_c)^2 for rows [0,nrows) of prop; returns
-// the number of column groups.  Block-level; prop must be visible; s.part is written but not synchronised on return
-// (the sampler's accept phase adds the groups behind its own barrier).
-__device__ inline int decomp_c_eval_parts(const DecompCSmem& s, const DecompCShape& sh, const double* __restrict__ prop,
-                                          int ndim, int nrows, int rows_pad) {
+// s.part[group][row] = sum over the group's columns of ((y_c - Z_c)/sigma_c)^2 for rows [0,nrows) of prop, nrows <= the
+// rows_cap of the plan.  Block-level; prop must be visible; s.part is written but not synchronised on return (the
+// sampler's accept phase adds the pl.ngroups groups behind its own barrier).
+__device__ inline void decomp_c_eval_parts(const DecompCSmem& s, const DecompCShape& sh, const DecompCPlan& pl,
+                                           const double* __restrict__ prop, int ndim, int nrows, int rows_pad) {
   switch (sh.D) {
-    case 1: return decomp_c_parts_d<1>(s, sh, prop, ndim, nrows, rows_pad);
-    case 2: return decomp_c_parts_d<2>(s, sh, prop, ndim, nrows, rows_pad);
-    case 3: return decomp_c_parts_d<3>(s, sh, prop, ndim, nrows, rows_pad);
-    case 4: return decomp_c_parts_d<4>(s, sh, prop, ndim, nrows, rows_pad);
-    case 5: return decomp_c_parts_d<5>(s, sh, prop, ndim, nrows, rows_pad);
-    case 6: return decomp_c_parts_d<6>(s, sh, prop, ndim, nrows, rows_pad);
-    case 7: return decomp_c_parts_d<7>(s, sh, prop, ndim, nrows, rows_pad);
-    default: return decomp_c_parts_d<8>(s, sh, prop, ndim, nrows, rows_pad);
+    case 1: decomp_c_parts_d<1>(s, sh, pl, prop, ndim, nrows, rows_pad); break;
+    case 2: decomp_c_parts_d<2>(s, sh, pl, prop, ndim, nrows, rows_pad); break;
+    case 3: decomp_c_parts_d<3>(s, sh, pl, prop, ndim, nrows, rows_pad); break;
+    case 4: decomp_c_parts_d<4>(s, sh, pl, prop, ndim, nrows, rows_pad); break;
+    case 5: decomp_c_parts_d<5>(s, sh, pl, prop, ndim, nrows, rows_pad); break;
+    case 6: decomp_c_parts_d<6>(s, sh, pl, prop, ndim, nrows, rows_pad); break;
+    case 7: decomp_c_parts_d<7>(s, sh, pl, prop, ndim, nrows, rows_pad); break;
+    default: decomp_c_parts_d<8>(s, sh, pl, prop, ndim, nrows, rows_pad); break;
   }
 }
 
 // chi[row] = sum_c ((y_c - Z_c)/sigma_c)^2 (batched log-probability kernel).  chi[] is written but not synchronised.
-__device__ inline void decomp_c_eval_chi(const DecompCSmem& s, const DecompCShape& sh, const double* __restrict__ prop,
-                                         int ndim, int nrows, int rows_pad, double* chi) {
-  const int ngroups = decomp_c_eval_parts(s, sh, prop, ndim, nrows, rows_pad);
+__device__ inline void decomp_c_eval_chi(const DecompCSmem& s, const DecompCShape& sh, const DecompCPlan& pl,
+                                         const double* __restrict__ prop, int ndim, int nrows, int rows_pad, double* chi) {
+  decomp_c_eval_parts(s, sh, pl, prop, ndim, nrows, rows_pad);
   __syncthreads();
   for (int p = threadIdx.x; p < nrows; p += blockDim.x) {
     double acc = 0.0;
-    for (int g = 0; g < ngroups; ++g) acc += s.part[(size_t)g * rows_pad + p];
+    for (int g = 0; g < pl.ngroups; ++g) acc += s.part[(size_t)g * rows_pad + p];
     chi[p] = acc;
   }
 }
