@@ -335,11 +335,15 @@ def run_gpu(args):
             variants[prec].update({"e2e_evals_per_s": B * WALKERS * NSTEPS / best, "e2e_spectra_per_s": B / best,
                                    "e2e_ms_per_step": 1e3 * best, "e2e_nan_flags": int((r_alt['flags'] != 0).sum())})
             if prec == "fp64-collapsed":
-                # FP64 to rounding: the sampler takes the same decisions as the two-stage DMMA path (`r` = last e2e result)
-                variants[prec]["summaries_identical_to_fp64"] = bool(
-                    np.array_equal(r_alt['percentiles'], r['percentiles'])
-                    and np.array_equal(r_alt['acceptance_fraction'], r['acceptance_fraction']))
-                variants[prec]["algorithmic_flop_per_eval"] = 2 * 2 * N_FREQ * (POLY_DEG + 1 + 2)
+                # FP64 to rounding: the sampler takes the same decisions as the two-stage DMMA path (`r` = last e2e
+                # result) unless a ~1e-13 log-prob rounding difference flips one of the shard's 1.3e10 accept tests
+                # (expected: a fraction of one spectrum per shard); from there on that spectrum's chain is a different,
+                # equally valid draw
+                same = np.all(r_alt['percentiles'] == r['percentiles'], axis=(1, 2))
+                shift = np.abs(r_alt['percentiles'][:, 1] - r['percentiles'][:, 1]) / r['std']
+                variants[prec].update({"spectra_with_percentiles_identical_to_fp64": int(same.sum()), "e2e_spectra": B,
+                                       "max_median_shift_in_posterior_sd": float(shift.max()),
+                                       "algorithmic_flop_per_eval": 2 * 2 * N_FREQ * (POLY_DEG + 1 + 2)})
             del r_alt, alt
     if rank == 0:
         k_ms = float(np.mean(kern_ms))

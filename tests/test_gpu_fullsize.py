@@ -105,6 +105,35 @@ def test_c3_full_size(model, min_cov):
     np.testing.assert_array_equal(r1['chain'][0], ref['chain'])
 
 
+def test_c5_shard_full_size_collapsed():
+    """The same full-size shard with precision='fp64-collapsed' (z = (L K) a, csrc/decomp_collapsed.cuh): calibrated,
+    independent of how the batch is cut, and — being FP64 to rounding — the SAME chains as the two-stage DMMA path:
+    summaries of a 512-spectra slice are identical except where a ~1e-13 log-prob rounding difference flipped one
+    of that slice's 5e8 accept tests (expected ~0.01 spectra; allowed: 1 %, and those within Monte-Carlo error)."""
+    from bisip_b200 import engine
+    from bisip_b200.batch import BatchInversion
+    B = 12500
+    ctor = dict(nwalkers=256, nsteps=2000, poly_deg=4, n_tau=64, seed=0xB151B, precision='fp64-collapsed')
+    fit_kw = dict(discard=1000, thin=10)
+    w, syn, truth = _make('decomp', B, poly_deg=4, n_tau=64)
+    inv = BatchInversion('decomp', w, syn['zn'], syn['zn_err'], **ctor)
+    assert engine.decomp_kernel_kind(inv._spec(), 64, 256) == 'fp64-collapsed'
+    res = inv.fit(**fit_kw)
+    assert np.all(res['flags'] == 0) and np.all(np.isfinite(res['mean'])) and np.all(res['std'] > 0)
+    acc = res['acceptance_fraction']
+    assert 0.40 < acc.min() and acc.max() < 0.60
+    cov, zm, zs = _calibration(res, truth)
+    assert np.all(np.abs(cov - 0.95) < 0.01), cov
+    assert np.all(np.abs(zm) < 0.15), zm
+    assert np.all(np.abs(zs - 1.0) < 0.05), zs
+    _subset_identical('decomp', w, syn, res, 6000, 6004, fit_kw, **ctor)
+    ref = BatchInversion('decomp', w, syn['zn'][:512], syn['zn_err'][:512], **dict(ctor, precision='fp64')).fit(**fit_kw)
+    same = np.all(res['percentiles'][:512] == ref['percentiles'], axis=(1, 2))
+    assert same.mean() >= 0.99, same.mean()
+    shift = np.abs(res['percentiles'][:512, 1] - ref['percentiles'][:, 1]) / ref['std']
+    assert shift.max() < 0.35, shift.max()
+
+
 @pytest.mark.parametrize("prec", ['3xtf32', 'tf32'])
 def test_c5_shard_full_size_tcgen05(prec):
     """The same full-size shard on the tcgen05 kernel (TF32 / 3xTF32 operands, FP32 accumulators in tensor memory):
