@@ -144,8 +144,6 @@ __global__ void __launch_bounds__(kThreads) decomp_c_batch_kernel(const BatchPar
   const int b = blockIdx.y, ndim = P.d.ndim, N = P.d.n_freq;
   DecompCShape sh(P.d.n_freq, P.d.n_tau, P.d.n_coef);
   DecompCSmem s;
-  DecompCPlan pl;
-  pl.make(kRows, N);
   double* p = decomp_c_carve(s, smem, sh, kRows);
   double* prop = p; p += kRows * ndim;
   double* chi = p; p += kRows;
@@ -163,7 +161,7 @@ __global__ void __launch_bounds__(kThreads) decomp_c_batch_kernel(const BatchPar
     if (WANT_Z) {
       decomp_c_eval_Z(s, sh, prop, ndim, n, P.Z + ((size_t)b * P.n_theta + r0) * 2 * N);
     } else {
-      decomp_c_eval_chi(s, sh, pl, prop, ndim, n, kRows, chi);
+      decomp_c_eval_chi(s, sh, prop, ndim, n, kRows, chi);
       __syncthreads();
       for (int q = threadIdx.x; q < n; q += kThreads)
         P.lp[(size_t)b * P.n_theta + r0 + q] =

@@ -114,30 +114,33 @@ __device__ inline void decomp_c_init(DecompCSmem& s, const DecompCShape& sh, dou
 #endif
 constexpr int kCRows = BISIP_COLLAPSED_RPT;
 
-// Work split of an evaluation, fixed once per CTA for the largest number of rows it will see (`rows_cap`; integer
-// divisions are ~40 instructions each and used to be 8 % of the kernel when this was redone per evaluation):
-// thread-rows (rpt proposals each) padded to whole warps so that a warp works on ONE column group, the real block and
-// the imaginary block each cut into `gh` column groups of `cpg` columns.  Thread t owns thread-rows tr0, tr0+tstep, ...
-// and groups g0, g0+gstep, ...; an evaluation of fewer rows leaves the threads of the missing rows idle.
+// Work split of an evaluation, a function of the largest number of rows the CTA evaluates (`rows_cap`) only:
+// thread-rows (rpt proposals each) padded to a power of two >= 32 so that a warp works on ONE column group, the real
+// block and the imaginary block each cut into `gh` (a power of two) column groups of `cpg` columns.  Thread t owns
+// thread-rows tr0, tr0+tstep, ... and groups g0, g0+gstep, ...; an evaluation of fewer rows leaves the threads of the
+// missing rows idle.  Shifts only (the CTA size is a power of two): it is rebuilt at every evaluation for ~20
+// integer instructions — integer divisions here were 8 % of the kernel, and a plan kept across the sampler's phases
+// was spilled and its reloads stalled the evaluation (long scoreboard, 5 % of the warp samples).
 struct DecompCPlan {
-  int rpt, trows, gh, cpg, ngroups, tr0, tstep, g0, gstep;
+  int rpt, trows, gh, lg_gh, cpg, ngroups, tr0, tstep, g0, gstep;
   __device__ __forceinline__ void make(int rows_cap, int N) {
     const int NT = blockDim.x, tid = threadIdx.x;
+    const int lg_nt = 31 - __clz(NT);
     rpt = (kCRows > 1 && rows_cap >= 32 * kCRows) ? kCRows : 1;
-    trows = ceil_div(rows_cap, rpt);
-    const int rows_p = (trows + 31) & ~31;
-    gh = NT / (2 * rows_p);
-    if (gh < 1) gh = 1;
-    if (gh > N) gh = N;
-    cpg = ceil_div(N, gh);
-    gh = ceil_div(N, cpg);
-    ngroups = 2 * gh;       // <= NT/32 <= kWarps
-    if (rows_p <= NT) {     // NT/rows_p >= ngroups groups side by side: one pass
-      gstep = NT / rows_p;
-      g0 = tid / rows_p;
-      tr0 = tid - g0 * rows_p;
-      tstep = rows_p;
-      if (g0 >= gstep) g0 = ngroups;   // leftover threads
+    trows = rpt > 1 ? (rows_cap + kCRows - 1) / kCRows : rows_cap;          // kCRows is a compile-time constant
+    const int lg = trows <= 32 ? 5 : 32 - __clz(trows - 1);                 // rows_p = 2^lg >= max(32, trows)
+    lg_gh = lg_nt - 1 - lg;
+    if (lg_gh < 0) lg_gh = 0;
+    const int lg_n = 31 - __clz(N);
+    if (lg_gh > lg_n) lg_gh = lg_n;                                         // at most N groups per block
+    gh = 1 << lg_gh;
+    cpg = (N + gh - 1) >> lg_gh;                                            // trailing groups may be empty
+    ngroups = 2 * gh;                                                       // <= NT/32 <= kWarps
+    if (lg <= lg_nt) {      // NT / rows_p >= ngroups groups side by side: one pass
+      gstep = NT >> lg;
+      g0 = tid >> lg;
+      tr0 = tid & ((1 << lg) - 1);
+      tstep = 1 << lg;
     } else {                // more thread-rows than threads: every thread walks all groups
       gstep = 1; g0 = 0; tr0 = tid; tstep = NT;
     }
@@ -184,7 +187,7 @@ __device__ __forceinline__ void decomp_c_parts_dr(const DecompCSmem& s, const De
       for (int i = 0; i < D; ++i) ra[r][i] = R0[r] * th[1 + i];
     }
     for (int grp = pl.g0; grp < pl.ngroups; grp += pl.gstep) {      // grp is warp-uniform
-      const int blk = grp >= pl.gh ? 1 : 0, gi = grp - blk * pl.gh;
+      const int blk = grp >> pl.lg_gh, gi = grp & (pl.gh - 1);
       const int c0 = blk * sh.N + gi * pl.cpg, c1 = blk * sh.N + min(sh.N, (gi + 1) * pl.cpg);
       if (blk) decomp_c_rows<D, RPT, false>(s.rec, c0, c1, R0, ra, x);
       else decomp_c_rows<D, RPT, true>(s.rec, c0, c1, R0, ra, x);
@@ -204,11 +207,13 @@ __device__ __forceinline__ void decomp_c_parts_d(const DecompCSmem& s, const Dec
   else decomp_c_parts_dr<D, 1>(s, sh, pl, prop, ndim, nrows, rows_pad);
 }
 
-// s.part[group][row] = sum over the group's columns of ((y_c - Z_c)/sigma_c)^2 for rows [0,nrows) of prop, nrows <= the
-// rows_cap of the plan.  Block-level; prop must be visible; s.part is written but not synchronised on return (the
-// sampler's accept phase adds the pl.ngroups groups behind its own barrier).
-__device__ inline void decomp_c_eval_parts(const DecompCSmem& s, const DecompCShape& sh, const DecompCPlan& pl,
-                                           const double* __restrict__ prop, int ndim, int nrows, int rows_pad) {
+// s.part[group][row] = sum over the group's columns of ((y_c - Z_c)/sigma_c)^2 for rows [0,nrows) of prop,
+// nrows <= rows_cap; returns the number of groups.  Block-level; prop must be visible; s.part is written but not
+// synchronised on return (the sampler's accept phase adds the groups behind its own barrier).
+__device__ inline int decomp_c_eval_parts(const DecompCSmem& s, const DecompCShape& sh, int rows_cap,
+                                          const double* __restrict__ prop, int ndim, int nrows, int rows_pad) {
+  DecompCPlan pl;
+  pl.make(rows_cap, sh.N);
   switch (sh.D) {
     case 1: decomp_c_parts_d<1>(s, sh, pl, prop, ndim, nrows, rows_pad); break;
     case 2: decomp_c_parts_d<2>(s, sh, pl, prop, ndim, nrows, rows_pad); break;
@@ -219,16 +224,24 @@ __device__ inline void decomp_c_eval_parts(const DecompCSmem& s, const DecompCSh
     case 7: decomp_c_parts_d<7>(s, sh, pl, prop, ndim, nrows, rows_pad); break;
     default: decomp_c_parts_d<8>(s, sh, pl, prop, ndim, nrows, rows_pad); break;
   }
+  return pl.ngroups;
+}
+
+// number of column groups decomp_c_eval_parts() produces for this rows_cap (the reader's side of the plan)
+__device__ __forceinline__ int decomp_c_ngroups(int rows_cap, int N) {
+  DecompCPlan pl;
+  pl.make(rows_cap, N);
+  return pl.ngroups;
 }
 
 // chi[row] = sum_c ((y_c - Z_c)/sigma_c)^2 (batched log-probability kernel).  chi[] is written but not synchronised.
-__device__ inline void decomp_c_eval_chi(const DecompCSmem& s, const DecompCShape& sh, const DecompCPlan& pl,
-                                         const double* __restrict__ prop, int ndim, int nrows, int rows_pad, double* chi) {
-  decomp_c_eval_parts(s, sh, pl, prop, ndim, nrows, rows_pad);
+__device__ inline void decomp_c_eval_chi(const DecompCSmem& s, const DecompCShape& sh, const double* __restrict__ prop,
+                                         int ndim, int nrows, int rows_pad, double* chi) {
+  const int ngroups = decomp_c_eval_parts(s, sh, rows_pad, prop, ndim, nrows, rows_pad);
   __syncthreads();
   for (int p = threadIdx.x; p < nrows; p += blockDim.x) {
     double acc = 0.0;
-    for (int g = 0; g < pl.ngroups; ++g) acc += s.part[(size_t)g * rows_pad + p];
+    for (int g = 0; g < ngroups; ++g) acc += s.part[(size_t)g * rows_pad + p];
     chi[p] = acc;
   }
 }

@@ -449,14 +449,13 @@ struct DecompCollapsedEvaluator {
   __device__ __forceinline__ void release() {}
   DecompCSmem sm;
   DecompCShape sh;
-  DecompCPlan pl;
   int rows_pad;
   __device__ DecompCollapsedEvaluator(const bisip_model_desc& d, int, int) : sh(d.n_freq, d.n_tau, d.n_coef) {}
   static __host__ size_t smem_doubles(const bisip_model_desc& d, int rows_pad) {
     return decomp_c_smem_doubles(DecompCShape(d.n_freq, d.n_tau, d.n_coef), rows_pad);
   }
   // rp = sampler_rows_pad(W) >= the rows of either half-step
-  __device__ double* carve(double* base, int rp) { rows_pad = rp; pl.make(rp, sh.N); return decomp_c_carve(sm, base, sh, rp); }
+  __device__ double* carve(double* base, int rp) { rows_pad = rp; return decomp_c_carve(sm, base, sh, rp); }
   __device__ void init(const bisip_model_desc& d, const double* w, const double* taus, const double* log_taus,
                        const double* y, const double* yerr, double* red) {
     decomp_c_init(sm, sh, d.c_exp, w, taus, log_taus, y, yerr, red);
@@ -465,14 +464,15 @@ struct DecompCollapsedEvaluator {
   // the per-column-group partial sums are added here, in group order, by the thread that takes the accept
   // decision: no reduction pass and no extra barrier inside the evaluation
   __device__ __forceinline__ double chi_of(const double*, int q) const {
+    const int ngroups = decomp_c_ngroups(rows_pad, sh.N);
     double acc = 0.0;
-    for (int g = 0; g < pl.ngroups; ++g) acc += sm.part[(size_t)g * rows_pad + q];
+    for (int g = 0; g < ngroups; ++g) acc += sm.part[(size_t)g * rows_pad + q];
     return acc;
   }
   __device__ int iters_per_warp(int) const { return 0; }
   __device__ void eval_chi(const double* prop, int ndim, int nrows, double* chi, RankSide& side) {
     side.finish();
-    decomp_c_eval_parts(sm, sh, pl, prop, ndim, nrows, rows_pad);
+    decomp_c_eval_parts(sm, sh, rows_pad, prop, ndim, nrows, rows_pad);
   }
 };
 
