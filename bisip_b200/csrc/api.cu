@@ -85,7 +85,8 @@ constexpr int kVecSmallW = 128;  // walkers up to which the 128-thread variant i
 #ifdef BISIP_COLLAPSED_MINB
 constexpr int kMinBCollapsed = BISIP_COLLAPSED_MINB;
 #else
-constexpr int kMinBCollapsed = 4;   // collapsed decomposition, 256-thread CTAs (64 registers)
+constexpr int kMinBCollapsed = 3;   // collapsed decomposition, 256-thread CTAs: 80 registers and no spills; at 4 per SM
+                                    // (64 registers) the spill reloads cost more than the fourth CTA hides (-4 %)
 #endif
 
 // launch ensemble_kernel<VecEvaluator<Row>> in the shape picked for W walkers; MB128 = CTAs/SM of the
@@ -631,8 +632,12 @@ int bisip_ensemble_run(const bisip_model_desc* desc, int n_spectra, int n_walker
     default: {
       if (desc->precision == BISIP_PREC_FP64_COLLAPSED) {
         smem += DecompCollapsedEvaluator::smem_doubles(*desc, rp) * 8;
-        if (n_walkers <= kVecSmallW)
+        // measured (profiles/r01h_collapsed_sweep.log): 32 walkers 4.6e9 evals/s at 8 CTAs/SM vs 4.1e9 at 6;
+        // 128 walkers 8.1e9 at 6 (80 registers, no spills) vs 6.7e9 at 8
+        if (n_walkers <= 64)
           return launch(ensemble_kernel<DecompCollapsedEvaluator, 8, 128>, grid, smem, st, "ensemble_decomp_collapsed", &P, 128);
+        if (n_walkers <= kVecSmallW)
+          return launch(ensemble_kernel<DecompCollapsedEvaluator, 6, 128>, grid, smem, st, "ensemble_decomp_collapsed", &P, 128);
         return launch(ensemble_kernel<DecompCollapsedEvaluator, kMinBCollapsed, kThreads>, grid, smem, st,
                       "ensemble_decomp_collapsed", &P, kThreads);
       }

@@ -115,27 +115,27 @@ __device__ inline void decomp_c_init(DecompCSmem& s, const DecompCShape& sh, dou
 constexpr int kCRows = BISIP_COLLAPSED_RPT;
 
 // Work split of an evaluation, a function of the largest number of rows the CTA evaluates (`rows_cap`) only:
-// thread-rows (rpt proposals each) padded to a power of two >= 32 so that a warp works on ONE column group, the real
-// block and the imaginary block each cut into `gh` (a power of two) column groups of `cpg` columns.  Thread t owns
+// thread-rows (rpt proposals each) padded to a power of two >= 32 so that a warp works on ONE group, the N frequencies
+// cut into `ngroups` (a power of two) groups of `fpg` frequencies — a group is the real columns AND the imaginary
+// columns of its frequencies, so every warp has the same work (real columns cost one FMA more).  Thread t owns
 // thread-rows tr0, tr0+tstep, ... and groups g0, g0+gstep, ...; an evaluation of fewer rows leaves the threads of the
 // missing rows idle.  Shifts only (the CTA size is a power of two): it is rebuilt at every evaluation for ~20
 // integer instructions — integer divisions here were 8 % of the kernel, and a plan kept across the sampler's phases
 // was spilled and its reloads stalled the evaluation (long scoreboard, 5 % of the warp samples).
 struct DecompCPlan {
-  int rpt, trows, gh, lg_gh, cpg, ngroups, tr0, tstep, g0, gstep;
+  int rpt, trows, fpg, ngroups, tr0, tstep, g0, gstep;
   __device__ __forceinline__ void make(int rows_cap, int N) {
     const int NT = blockDim.x, tid = threadIdx.x;
     const int lg_nt = 31 - __clz(NT);
     rpt = (kCRows > 1 && rows_cap >= 32 * kCRows) ? kCRows : 1;
     trows = rpt > 1 ? (rows_cap + kCRows - 1) / kCRows : rows_cap;          // kCRows is a compile-time constant
     const int lg = trows <= 32 ? 5 : 32 - __clz(trows - 1);                 // rows_p = 2^lg >= max(32, trows)
-    lg_gh = lg_nt - 1 - lg;
-    if (lg_gh < 0) lg_gh = 0;
+    int lg_g = lg_nt - lg;                                                  // NT / rows_p groups fill the CTA
+    if (lg_g < 0) lg_g = 0;
     const int lg_n = 31 - __clz(N);
-    if (lg_gh > lg_n) lg_gh = lg_n;                                         // at most N groups per block
-    gh = 1 << lg_gh;
-    cpg = (N + gh - 1) >> lg_gh;                                            // trailing groups may be empty
-    ngroups = 2 * gh;                                                       // <= NT/32 <= kWarps
+    if (lg_g > lg_n) lg_g = lg_n;                                           // at most N groups
+    ngroups = 1 << lg_g;                                                    // <= NT/32 <= kWarps
+    fpg = (N + ngroups - 1) >> lg_g;                                        // trailing groups may be empty
     if (lg <= lg_nt) {      // NT / rows_p >= ngroups groups side by side: one pass
       gstep = NT >> lg;
       g0 = tid >> lg;
@@ -147,31 +147,42 @@ struct DecompCPlan {
   }
 };
 
-// RPT proposals x one column group: chi[r] = sum_c ((y_c - Z_c)/sigma_c)^2 over columns [c0, c1)
+// RPT proposals x a run of columns: chi[r] += sum_c ((y_c - Z_c)/sigma_c)^2 over columns [c0, c1)
+template <int D, int RPT, bool REAL>
+__device__ __forceinline__ void decomp_c_col(const double2 (&u)[(2 + D + 1) / 2], const double (&R0)[RPT],
+                                             const double (&ra)[RPT][D], double (&chi)[RPT]) {
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) {
+    double a = REAL ? fma(-R0[r], u[0].y, u[0].x) : u[0].x;
+#pragma unroll
+    for (int i = 0; i < D; ++i) a = fma(ra[r][i], ((i & 1) ? u[1 + (i >> 1)].y : u[1 + (i >> 1)].x), a);
+    chi[r] = fma(a, a, chi[r]);
+  }
+}
+
+// explicit shared-memory load: through the struct-held generic pointer the compiler falls back to LD.E.128
+__device__ __forceinline__ double2 lds_f64x2(uint32_t saddr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(saddr));
+  return v;
+}
+
 template <int D, int RPT, bool REAL>
 __device__ __forceinline__ void decomp_c_rows(const double* __restrict__ rec, int c0, int c1, const double (&R0)[RPT],
                                               const double (&ra)[RPT][D], double (&chi)[RPT]) {
-  const double2* r2 = reinterpret_cast<const double2*>(rec);
-  constexpr int kV = kCRec / 2;             // double2 per record
+  const uint32_t r2 = (uint32_t)__cvta_generic_to_shared(rec);
+  constexpr int kV = kCRec * 8;             // bytes per record
   constexpr int kL = (2 + D + 1) / 2;       // double2 actually needed
-#pragma unroll
-  for (int r = 0; r < RPT; ++r) chi[r] = 0.0;
 #pragma unroll 2
   for (int c = c0; c < c1; ++c) {
     double2 u[kL];
 #pragma unroll
-    for (int q = 0; q < kL; ++q) u[q] = r2[(size_t)c * kV + q];
-#pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-      double a = REAL ? fma(-R0[r], u[0].y, u[0].x) : u[0].x;
-#pragma unroll
-      for (int i = 0; i < D; ++i) a = fma(ra[r][i], ((i & 1) ? u[1 + (i >> 1)].y : u[1 + (i >> 1)].x), a);
-      chi[r] = fma(a, a, chi[r]);
-    }
+    for (int q = 0; q < kL; ++q) u[q] = lds_f64x2(r2 + c * kV + 16 * q);
+    decomp_c_col<D, RPT, REAL>(u, R0, ra, chi);
   }
 }
 
-// Partial chi^2 of every (proposal, column group) into s.part[group][row].  No barrier.
+// Partial chi^2 of every (proposal, frequency group) into s.part[group][row].  No barrier.
 template <int D, int RPT>
 __device__ __forceinline__ void decomp_c_parts_dr(const DecompCSmem& s, const DecompCShape& sh, const DecompCPlan& pl,
                                                   const double* __restrict__ prop, int ndim, int nrows, int rows_pad) {
@@ -187,10 +198,11 @@ __device__ __forceinline__ void decomp_c_parts_dr(const DecompCSmem& s, const De
       for (int i = 0; i < D; ++i) ra[r][i] = R0[r] * th[1 + i];
     }
     for (int grp = pl.g0; grp < pl.ngroups; grp += pl.gstep) {      // grp is warp-uniform
-      const int blk = grp >> pl.lg_gh, gi = grp & (pl.gh - 1);
-      const int c0 = blk * sh.N + gi * pl.cpg, c1 = blk * sh.N + min(sh.N, (gi + 1) * pl.cpg);
-      if (blk) decomp_c_rows<D, RPT, false>(s.rec, c0, c1, R0, ra, x);
-      else decomp_c_rows<D, RPT, true>(s.rec, c0, c1, R0, ra, x);
+      const int f0 = grp * pl.fpg, f1 = min(sh.N, f0 + pl.fpg);
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) x[r] = 0.0;
+      decomp_c_rows<D, RPT, true>(s.rec, f0, f1, R0, ra, x);
+      decomp_c_rows<D, RPT, false>(s.rec, sh.N + f0, sh.N + f1, R0, ra, x);
 #pragma unroll
       for (int r = 0; r < RPT; ++r) {
         const int row = tr + r * pl.trows;
