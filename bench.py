@@ -359,7 +359,15 @@ def run_gpu(args):
                 traffic = None
         # CPU baseline (bounded sample of the same spectra, all host cores)
         cores = host_cores()
-        cpu_v, cpu_wall, cpu_sample = reference_sample(syn['zn'], syn['zn_err'], syn['w'], min(cores, B))
+        if world == 1:
+            cpu_v, cpu_wall, cpu_sample = reference_sample(syn['zn'], syn['zn_err'], syn['w'], min(cores, B))
+            cpu_baseline = {"value": cpu_v, "unit": "evals/s", "cores": min(cores, B), "kind": "reference", "sample": cpu_sample,
+                            "wall_s": cpu_wall, "evals_per_s_per_core": cpu_v / min(cores, B),
+                            "extrapolated_days_for_full_config_on_these_cores": 1e5 * WALKERS * NSTEPS / cpu_v / 86400.0,
+                            "note": "reference models.py + Cython (oracle/_ref) under oracle/emcee_restatement.py"}
+        else:       # the host-core baseline is a property of the box, not of N: timed at N=1 only (the other ranks would wait)
+            cpu_baseline = {"value": None, "unit": "evals/s", "cores": cores, "kind": "reference",
+                            "sample": "not run at N>1: see the N=1 line"}
         line = {
             "metric": "log-prob evals/sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -381,10 +389,7 @@ def run_gpu(args):
                          "peak_source": peak_src, "peak_burst": peak_burst,
                          "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_step,
                          "algorithmic_flop_per_eval": FLOP_PER_EVAL},
-            "cpu_baseline": {"value": cpu_v, "unit": "evals/s", "cores": min(cores, B), "kind": "reference", "sample": cpu_sample,
-                             "wall_s": cpu_wall, "evals_per_s_per_core": cpu_v / min(cores, B),
-                             "extrapolated_days_for_full_config_on_these_cores": 1e5 * WALKERS * NSTEPS / cpu_v / 86400.0,
-                             "note": "reference models.py + Cython (oracle/_ref) under oracle/emcee_restatement.py"},
+            "cpu_baseline": cpu_baseline,
             "clocks": clk, "acceptance_fraction": acc, "nan_flags": flags_bad,
             "variants": {"note": "other decomposition kernels on the same shard: evals_per_s = ensemble kernel alone on a slice (CUDA "
                                  "events), e2e_* = the whole shard through BatchInversion.fit like `e2e`.  fp64-collapsed is FP64 "

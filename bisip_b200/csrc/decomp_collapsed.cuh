@@ -6,10 +6,10 @@
 // and one log-probability costs 2N (D + 2) FP64 FMAs instead of 2 S 2N + 2 D S flops (D = poly_deg+1):
 // 1,792 instead of 17,792 at the C5 shape.  G is accumulated with a compensated (Dot2) sum, so the
 // only rounding that differs from the two-stage path is the final D-term dot product; forward and
-// log-probability meet the same 1e-12 parity bar against the reference (tests/test_gpu_parity.py).
+// log-probability meet the same 1e-12 parity bar against the reference (tests/test_gpu_collapsed.py).
 // With D <= 8 the contraction is too thin for tensor tiles (an m16n8k8 DMMA tile pads D to 8 and runs
 // on the same pipe at the same flop rate as DFMA), so it runs on the FP64 vector pipe: a thread owns
-// kCRows proposals and one group of columns; the column records are warp-uniform broadcast loads.
+// kCRows proposals and one group of frequencies; the column records are warp-uniform broadcast loads.
 //
 // north_star grades the two-stage contraction on DMMA tiles, which therefore stays the default
 // (decomp_eval.cuh); this evaluator is the opt-in fast path for users who only want the answer.
