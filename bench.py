@@ -36,6 +36,25 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE line, the JSON result: native libraries (NCCL's version banner under NCCL_DEBUG, ncu,
+# the CUDA runtime) print to file descriptor 1 behind Python's back, so fd 1 is pointed at stderr for the whole run
+# and the JSON line goes to a private duplicate of the original stdout.
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
 # ---- workload (BASELINE config 5 shard) ------------------------------------------------------
 N_FREQ, N_TAU, POLY_DEG, WALKERS, NSTEPS = 64, 64, 4, 256, 2000
 SPECTRA_PER_GPU = int(os.environ.get("BISIP_BENCH_SPECTRA", 12500))
@@ -132,7 +151,7 @@ def run_reference(args):
     pool.close()
     val = float(np.mean(rates))
     kind = "reference"
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": "log-prob evals/sec", "value": val, "unit": "evals/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(walls)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -397,7 +416,7 @@ def run_gpu(args):
                                  "value / e2e / roofline above are the default two-stage FP64 DMMA path",
                          "fp64_evals_per_s_kernel": evals_step / world * (NSTEPS + 1) / NSTEPS / (k_ms * 1e-3), **variants},
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -415,6 +434,7 @@ def main():
         os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                                    f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                                    "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:])
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
