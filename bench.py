@@ -318,6 +318,22 @@ def run_gpu(args):
     # ---- reduced-precision variants of the same workload (north_star: "a TF32/3xTF32 variant compared against it"):
     #      the tcgen05 kernel on a 592-spectra slice of this rank's shard, ensemble kernel alone, CUDA events.
     #      Reported next to the FP64 numbers; `value`, `e2e` and `roofline` stay FP64.
+    # ---- the collapsed FP64 path end to end on EVERY rank (weak scaling of the fast path: at N=8 this is the whole
+    #      100,000-spectra survey), max over ranks like `e2e`
+    alt = BatchInversion('decomp', syn['w'], zn_h, ze_h, nwalkers=WALKERS, nsteps=NSTEPS, poly_deg=POLY_DEG,
+                         n_tau=N_TAU, seed=SEED, spectrum_offset=b0, device=dev, precision='fp64-collapsed')
+    col_best = 1e30
+    for rep in range(2):
+        barrier()
+        t0 = time.perf_counter()
+        r_col = alt.fit(p0=p0_h, discard=DISCARD, thin=THIN, percentiles=PCT)
+        torch.cuda.synchronize()
+        tc = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        col_best = min(col_best, float(tc.item()))
+    del alt
+
     variants = {}
     if rank == 0:
         for prec in ("fp64-collapsed", "3xtf32", "tf32"):
@@ -341,29 +357,31 @@ def run_gpu(args):
                               "nan_flags": int((r_alt['flags'] != 0).sum().item())}
             del r_alt
         # the whole shard end to end through the public API (pinned host inputs, host summaries), like `e2e`
-        for prec in ("fp64-collapsed", "3xtf32"):
-            alt = BatchInversion('decomp', syn['w'], zn_h, ze_h, nwalkers=WALKERS, nsteps=NSTEPS, poly_deg=POLY_DEG,
-                                 n_tau=N_TAU, seed=SEED, spectrum_offset=b0, device=dev, precision=prec)
-            best = 1e30
-            for rep in range(2):
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                r_alt = alt.fit(p0=p0_h, discard=DISCARD, thin=THIN, percentiles=PCT)
-                torch.cuda.synchronize()
-                best = min(best, time.perf_counter() - t0)
-            variants[prec].update({"e2e_evals_per_s": B * WALKERS * NSTEPS / best, "e2e_spectra_per_s": B / best,
-                                   "e2e_ms_per_step": 1e3 * best, "e2e_nan_flags": int((r_alt['flags'] != 0).sum())})
-            if prec == "fp64-collapsed":
-                # FP64 to rounding: the sampler takes the same decisions as the two-stage DMMA path (`r` = last e2e
-                # result) unless a ~1e-13 log-prob rounding difference flips one of the shard's 1.3e10 accept tests
-                # (expected: a fraction of one spectrum per shard); from there on that spectrum's chain is a different,
-                # equally valid draw
-                same = np.all(r_alt['percentiles'] == r['percentiles'], axis=(1, 2))
-                shift = np.abs(r_alt['percentiles'][:, 1] - r['percentiles'][:, 1]) / r['std']
-                variants[prec].update({"spectra_with_percentiles_identical_to_fp64": int(same.sum()), "e2e_spectra": B,
-                                       "max_median_shift_in_posterior_sd": float(shift.max()),
-                                       "algorithmic_flop_per_eval": 2 * 2 * N_FREQ * (POLY_DEG + 1 + 2)})
-            del r_alt, alt
+        alt = BatchInversion('decomp', syn['w'], zn_h, ze_h, nwalkers=WALKERS, nsteps=NSTEPS, poly_deg=POLY_DEG,
+                             n_tau=N_TAU, seed=SEED, spectrum_offset=b0, device=dev, precision='3xtf32')
+        best = 1e30
+        for rep in range(2):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r_alt = alt.fit(p0=p0_h, discard=DISCARD, thin=THIN, percentiles=PCT)
+            torch.cuda.synchronize()
+            best = min(best, time.perf_counter() - t0)
+        variants['3xtf32'].update({"e2e_evals_per_s": B * WALKERS * NSTEPS / best, "e2e_spectra_per_s": B / best,
+                                   "e2e_ms_per_step": 1e3 * best, "e2e_nan_flags": int((r_alt['flags'] != 0).sum()),
+                                   "e2e_gpus": 1})
+        del r_alt, alt
+        # FP64 to rounding: the collapsed sampler takes the same decisions as the two-stage DMMA path (`r` = last e2e
+        # result of this rank) unless a ~1e-13 log-prob rounding difference flips one of the shard's 1.3e10 accept tests
+        # (expected: a fraction of one spectrum per shard); from there on that spectrum's chain is a different, equally
+        # valid draw
+        same = np.all(r_col['percentiles'] == r['percentiles'], axis=(1, 2))
+        shift = np.abs(r_col['percentiles'][:, 1] - r['percentiles'][:, 1]) / r['std']
+        variants['fp64-collapsed'].update({
+            "e2e_evals_per_s": B * world * WALKERS * NSTEPS / col_best, "e2e_spectra_per_s": B * world / col_best,
+            "e2e_ms_per_step": 1e3 * col_best, "e2e_nan_flags": int((r_col['flags'] != 0).sum()), "e2e_gpus": world,
+            "e2e_spectra": B * world, "spectra_with_percentiles_identical_to_fp64": int(same.sum()),
+            "spectra_compared": B, "max_median_shift_in_posterior_sd": float(shift.max()),
+            "algorithmic_flop_per_eval": 2 * 2 * N_FREQ * (POLY_DEG + 1 + 2)})
     if rank == 0:
         k_ms = float(np.mean(kern_ms))
         flops_launch = FLOP_PER_EVAL * float(B) * WALKERS * (NSTEPS + 1)       # +1: log-prob of p0

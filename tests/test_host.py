@@ -264,3 +264,23 @@ def test_gather_two_ranks_gloo(tmp_path):
         out, _ = p.communicate(timeout=180)
         assert p.returncode == 0, out
         assert "ok" in out
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver launches next to the GPU arm): stdout is exactly one JSON
+    line with the contract's keys, whatever the workers or native libraries print; ranks other than 0 print nothing."""
+    import json
+    env = dict(os.environ, BISIP_BENCH_REF_STEPS='2')
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1'],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = out.stdout.splitlines()
+    assert len(lines) == 1, lines
+    j = json.loads(lines[0])
+    assert j['impl'] == 'reference' and j['metric'] == 'log-prob evals/sec' and j['unit'] == 'evals/s'
+    assert j['value'] > 0 and j['higher_is_better'] is True and j['vs_baseline'] is None
+    assert j['cpu_baseline']['kind'] == 'reference' and j['cpu_baseline']['cores'] >= 1
+    assert j['e2e'] == {'value': j['value'], 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    quiet = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1'],
+                           capture_output=True, text=True, env=dict(env, RANK='1', WORLD_SIZE='2'), timeout=600)
+    assert quiet.returncode == 0 and quiet.stdout == ''
