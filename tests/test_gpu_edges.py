@@ -69,6 +69,51 @@ def test_shape_sweep_chain_matches_oracle(model, N, W, T, kw):
     assert res['acceptance_fraction'][0] == pytest.approx(ref['accepted'].mean() / T, abs=1e-15)
 
 
+COLLAPSED_SHAPES = [
+    # N, W, T, kwargs — every coefficient count the collapsed kernel is templated on (poly_deg 0..7), every work split:
+    # one / two proposals per thread, 128- and 256-thread CTAs, fewer rows than a warp, more thread-rows than threads,
+    # frequency groups that do not divide N, tau grids of any size (no cluster, no tau limit in this form)
+    (64, 256, 10, dict(poly_deg=0, n_tau=64)),
+    (20, 24, 60, dict(poly_deg=7, n_tau=40)),
+    (64, 64, 30, dict(poly_deg=3, n_tau=33)),
+    (7, 18, 50, dict(poly_deg=2, n_tau=9, c_exp=0.5)),
+    (64, 40, 20, dict(poly_deg=4, n_tau=65)),
+    (31, 258, 6, dict(poly_deg=5, n_tau=200, c_exp=0.7)),
+    (37, 128, 20, dict(poly_deg=1, n_tau=50)),
+    (64, 129, 12, dict(poly_deg=6, n_tau=128)),
+    (5, 14, 40, dict(poly_deg=4, n_tau=12)),
+    (64, 1100, 4, dict(poly_deg=4, n_tau=64)),
+    (3, 600, 5, dict(poly_deg=2, n_tau=300)),
+]
+
+
+@pytest.mark.parametrize("N,W,T,kw", COLLAPSED_SHAPES, ids=[f"N{s[0]}-W{s[1]}-P{s[3]['poly_deg']}" for s in COLLAPSED_SHAPES])
+def test_collapsed_shape_sweep_chain_matches_oracle(N, W, T, kw):
+    """precision='fp64-collapsed' (csrc/decomp_collapsed.cuh) over the shape classes of its work split: the chain is
+    the oracle's on the same Philox stream and the stored log-probabilities agree to 1e-12."""
+    from bisip_b200 import engine
+    from bisip_b200.batch import BatchInversion
+    from oracle import oracle
+    rng = np.random.default_rng(N * 1000 + W)
+    w, zn, ze, bounds, okw = _spectrum('decomp', N, rng, **kw)
+    inv = BatchInversion('decomp', w, zn[None], ze[None], nwalkers=W, nsteps=T, seed=99, spectrum_offset=7,
+                         precision='fp64-collapsed', **kw)
+    assert engine.decomp_kernel_kind(inv._spec(), N, W) == 'fp64-collapsed'
+    p0 = inv.draw_p0(0, 1)
+    res = inv.fit(p0=p0, keep_chain=True)
+    ref = oracle.Problem('decomp', w, zn, ze, bounds, **okw).run(p0[0], T, seed=99, spectrum=7)
+    assert res['flags'][0] == 0 and not ref['nan']
+    np.testing.assert_array_equal(res['chain'][0], ref['chain'])
+    fin = np.isfinite(ref['log_prob'])
+    assert np.array_equal(fin, np.isfinite(res['log_prob'][0]))
+    assert np.max(np.abs(res['log_prob'][0][fin] - ref['log_prob'][fin]) / np.maximum(1, np.abs(ref['log_prob'][fin]))) <= 1e-12
+    # forward through the batched kernel on the chain's last ensemble (ragged chunk: W is rarely a multiple of 128)
+    th = res['chain'][0][-1]
+    Z = engine.forward(inv._spec(), inv._to_dev(th[None], 0, 1), inv._to_dev(w[None], 0, 1)[0]).cpu().numpy()[0]
+    Zo = oracle.Problem('decomp', w, zn, ze, bounds, **okw).forward(th)
+    assert (np.max(np.abs(Z - Zo), axis=(1, 2)) / np.max(np.abs(Zo), axis=(1, 2))).max() <= 1e-12
+
+
 def test_per_spectrum_grids_and_non_pow2_scale():
     """w (B,N) and the tau grids differ per spectrum (w_stride / tau_stride paths); a = 2.5 takes the
     true-division branch of the stretch factor."""

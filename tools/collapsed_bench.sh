@@ -4,7 +4,7 @@
 cd "$(dirname "$0")/.."
 O=gpurun_out/${ROUND:-r01h}; mkdir -p $O
 timeout 300 python -m pytest tests/test_gpu_collapsed.py -x -q 2>&1 | tail -2
-for v in default ${VARIANTS:-e a b c d}; do
+for v in default ${VARIANTS:-}; do
   lib=$PWD/bisip_b200/csrc/libbisip_b200_$v.so
   [ $v = default ] && lib=$PWD/bisip_b200/csrc/libbisip_b200.so
   [ -f $lib ] || continue
