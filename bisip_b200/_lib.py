@@ -102,6 +102,29 @@ def dev_f64(a, device):
     return torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64))).to(device)
 
 
+_CONST_CACHE = {}
+_CONST_CACHE_MAX = 128
+
+
+def dev_const(a, device):
+    """Device copy of a small read-only host array (w, zn, zn_err, taus, log_taus, bounds), cached by content:
+    the single-spectrum API (``forward`` / ``_log_probability`` called in a loop, e.g. by an optimiser) would
+    otherwise re-upload the same constants on every call.  The cached tensors must not be written to."""
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device, dtype=torch.float64).contiguous()
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    if a.nbytes > (1 << 16):
+        return torch.from_numpy(a).to(device)
+    key = (str(device), a.shape, a.tobytes())
+    t = _CONST_CACHE.get(key)
+    if t is None:
+        if len(_CONST_CACHE) >= _CONST_CACHE_MAX:
+            _CONST_CACHE.pop(next(iter(_CONST_CACHE)))
+        t = torch.from_numpy(a).to(device)
+        _CONST_CACHE[key] = t
+    return t
+
+
 def ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 

@@ -31,6 +31,24 @@ int fail(int code, const std::string& msg) {
       return fail(BISIP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));        \
   } while (0)
 
+// The kernels must run on the device that owns the caller's buffers, whatever device is current in the calling
+// thread (one host thread may drive several GPUs): the entry points switch to the device of their primary pointer
+// and restore the previous one on return.  A host pointer / unknown pointer leaves the current device alone.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(const void* p) {
+    cudaPointerAttributes at;
+    if (p == nullptr || cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return; }
+    if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) return;
+    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; return; }
+    if (at.device != prev) switched = (cudaSetDevice(at.device) == cudaSuccess);
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 int check_desc(const bisip_model_desc* d) {
   if (!d) return fail(BISIP_ERR_BAD_ARG, "desc is null");
   if (d->n_freq <= 0) return fail(BISIP_ERR_BAD_ARG, "n_freq must be positive");
@@ -552,6 +570,7 @@ int bisip_forward(const bisip_model_desc* desc, int n_spectra, int n_theta, cons
   if (n_spectra <= 0 || n_theta <= 0 || !theta || !w || !Z) return fail(BISIP_ERR_BAD_ARG, "bisip_forward: bad argument");
   if (desc->model == BISIP_MODEL_DECOMP && (!taus || !log_taus)) return fail(BISIP_ERR_BAD_ARG, "bisip_forward: taus/log_taus null");
   if (n_spectra > 65535) return fail(BISIP_ERR_UNSUPPORTED, "bisip_forward: n_spectra > 65535 per call");
+  DeviceGuard guard(theta);
   BatchParams P{*desc, n_spectra, n_theta, theta, w, w_stride, taus, log_taus, tau_stride, nullptr, nullptr, nullptr, Z, nullptr};
   return run_batch<true>(P, (cudaStream_t)stream);
 }
@@ -565,6 +584,7 @@ int bisip_log_probability(const bisip_model_desc* desc, int n_spectra, int n_the
     return fail(BISIP_ERR_BAD_ARG, "bisip_log_probability: bad argument");
   if (desc->model == BISIP_MODEL_DECOMP && (!taus || !log_taus)) return fail(BISIP_ERR_BAD_ARG, "bisip_log_probability: taus/log_taus null");
   if (n_spectra > 65535) return fail(BISIP_ERR_UNSUPPORTED, "bisip_log_probability: n_spectra > 65535 per call");
+  DeviceGuard guard(theta);
   BatchParams P{*desc, n_spectra, n_theta, theta, w, w_stride, taus, log_taus, tau_stride, y, yerr, bounds, nullptr, lp_out};
   return run_batch<false>(P, (cudaStream_t)stream);
 }
@@ -572,6 +592,7 @@ int bisip_log_probability(const bisip_model_desc* desc, int n_spectra, int n_the
 int bisip_decomp_build_kernel(const double* w, int n_freq, const double* taus, int n_tau, double c_exp, double* K,
                               void* stream) {
   if (!w || !taus || !K || n_freq <= 0 || n_tau <= 0) return fail(BISIP_ERR_BAD_ARG, "bisip_decomp_build_kernel: bad argument");
+  DeviceGuard guard(K);
   build_kernel_matrix<<<ceil_div(n_freq * n_tau, 256), 256, 0, (cudaStream_t)stream>>>(w, n_freq, taus, n_tau, c_exp, K);
   BISIP_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
@@ -588,6 +609,7 @@ int bisip_ensemble_run(const bisip_model_desc* desc, int n_spectra, int n_walker
     return fail(BISIP_ERR_BAD_ARG, "bisip_ensemble_run: bad argument");
   if (desc->model == BISIP_MODEL_DECOMP && (!taus || !log_taus)) return fail(BISIP_ERR_BAD_ARG, "bisip_ensemble_run: taus/log_taus null");
   if (!(a > 1.0)) return fail(BISIP_ERR_BAD_ARG, "bisip_ensemble_run: stretch scale a must be > 1");
+  DeviceGuard guard(coords);
   cudaStream_t st = (cudaStream_t)stream;
   EnsembleParams P;
   P.d = *desc; P.B = n_spectra; P.W = n_walkers; P.nsteps = nsteps; P.step0 = step0; P.seed = seed;
@@ -701,6 +723,7 @@ int bisip_column_stats(const double* data, int n_spectra, int64_t n_samples, int
   if (workspace_bytes < bisip_column_stats_workspace(n_spectra, n_samples, n_cols))
     return fail(BISIP_ERR_BAD_ARG, "bisip_column_stats: workspace too small");
   if (n_spectra > 65535) return fail(BISIP_ERR_UNSUPPORTED, "bisip_column_stats: n_spectra > 65535 per call");
+  DeviceGuard guard(data);
   cudaStream_t st = (cudaStream_t)stream;
   StatsParams P;
   P.data = data; P.keys = (unsigned long long*)workspace; P.n = n_samples; P.ncol = n_cols; P.B = n_spectra;

@@ -71,7 +71,7 @@ class Inversion(_plotlib.plotlib, _utils.utils):
         (or (n, 2, N) for a (n, ndim) batch of parameter vectors)."""
         dev = _lib.require_cuda(self.device)
         th, single = self._theta_batch(theta, dev)
-        Z = engine.forward(self._spec(dev), th, _lib.dev_f64(w, dev))[0].cpu().numpy()
+        Z = engine.forward(self._spec(dev), th, _lib.dev_const(w, dev))[0].cpu().numpy()
         return Z[0] if single else Z
 
     def _log_probability(self, theta, model, bounds, x, y, yerr):
@@ -80,10 +80,10 @@ class Inversion(_plotlib.plotlib, _utils.utils):
         self._require_own_forward(model)
         dev = _lib.require_cuda(self.device)
         th, single = self._theta_batch(theta, dev)
-        lp = engine.log_probability(self._spec(dev), th, _lib.dev_f64(x, dev),
-                                    _lib.dev_f64(y, dev).reshape(1, 2, -1),
-                                    _lib.dev_f64(yerr, dev).reshape(1, 2, -1),
-                                    _lib.dev_f64(bounds, dev))[0].cpu().numpy()
+        lp = engine.log_probability(self._spec(dev), th, _lib.dev_const(x, dev),
+                                    _lib.dev_const(y, dev).reshape(1, 2, -1),
+                                    _lib.dev_const(yerr, dev).reshape(1, 2, -1),
+                                    _lib.dev_const(bounds, dev))[0].cpu().numpy()
         return float(lp[0]) if single else lp
 
     def _log_likelihood(self, theta, f, x, y, yerr):
@@ -217,7 +217,7 @@ class PolynomialDecomposition(Inversion):
 
     def _spec(self, dev):
         return engine.ModelSpec(model=self._model_id, ndim=1 + self.log_taus.shape[0],
-                                taus=_lib.dev_f64(self.taus, dev), log_taus=_lib.dev_f64(self.log_taus, dev),
+                                taus=_lib.dev_const(self.taus, dev), log_taus=_lib.dev_const(self.log_taus, dev),
                                 c_exp=float(self.c_exp), precision=_lib.PRECISIONS[self.precision])
 
     def forward(self, theta, w):

@@ -55,4 +55,4 @@ def test_run(dias=True, colecole=True, debye=True, nsteps_scale=1.0):
     print('All tests passed.')
 
 
-test_run.__test__ = False   # not a pytest test: it needs a GPU and is run by tests/test_gpu_api.py
+test_run.__test__ = False   # not a pytest test: it needs a GPU and is run by tests/test_gpu_emcee_anchors.py::test_package_test_run_executes

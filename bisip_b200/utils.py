@@ -25,7 +25,7 @@ class utils(object):
         chain = self.parse_chain(chain, **kwargs)
         dev = _lib.require_cuda(getattr(self, "device", None))
         th = _lib.dev_f64(chain, dev).reshape(1, -1, chain.shape[-1])
-        Z = engine.forward(self._spec(dev), th, _lib.dev_f64(self.data['w'], dev))   # (1, n, 2, N)
+        Z = engine.forward(self._spec(dev), th, _lib.dev_const(self.data['w'], dev))   # (1, n, 2, N)
         n, N = Z.shape[1], Z.shape[3]
         out = engine.column_stats(Z.reshape(1, n, 2 * N), p=p)["pct"][0]
         res = out.reshape(-1, 2, N).cpu().numpy()
