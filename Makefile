@@ -8,12 +8,21 @@ HDRS      := $(wildcard $(CSRC)/*.cuh) include/bisip_b200.h
 
 all: $(LIB) tools/peaks oracle
 
-$(LIB): $(CSRC)/api.cu $(HDRS)
-	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CSRC)/api.cu 2> $(CSRC)/ptxas.log || (cat $(CSRC)/ptxas.log; false)
+# One object per kernel family so that they compile in parallel (`make -j`); no device code crosses a
+# translation unit, so a plain host link is enough.  ptxas -v output of every unit is kept in $(CSRC)/ptxas.log.
+UNITS     := api ens_dmma ens_rc ens_umma ens_collapsed ens_colecole ens_dias_shin batch_decomp batch_vec
+OBJS      := $(UNITS:%=$(CSRC)/%.o)
+
+$(CSRC)/%.o: $(CSRC)/%.cu $(HDRS)
+	$(NVCC) $(NVCCFLAGS) $(EXTRA) -c -o $@ $< 2> $(CSRC)/$*.ptxas || (cat $(CSRC)/$*.ptxas; false)
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS)
+	cat $(UNITS:%=$(CSRC)/%.ptxas) > $(CSRC)/ptxas.log
 
 # developer build with per-phase cycle counters (not shipped, not loaded by the package)
-dbg: $(CSRC)/api.cu $(HDRS)
-	$(NVCC) $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared -DBISIP_PHASE_TIMING -o $(CSRC)/libbisip_b200_dbg.so $(CSRC)/api.cu
+dbg: $(HDRS)
+	$(NVCC) $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared -DBISIP_PHASE_TIMING -o $(CSRC)/libbisip_b200_dbg.so $(UNITS:%=$(CSRC)/%.cu)
 
 tools/peaks: tools/peaks.cu
 	$(NVCC) $(ARCH) -O3 -lineinfo -o $@ $<
@@ -23,7 +32,7 @@ oracle:
 	./oracle/build_ref.sh
 
 clean:
-	rm -f $(LIB) tools/peaks $(CSRC)/ptxas.log
+	rm -f $(LIB) $(OBJS) $(CSRC)/*.ptxas tools/peaks $(CSRC)/ptxas.log
 	rm -rf oracle/_build
 
 .PHONY: all oracle clean dbg

@@ -18,11 +18,12 @@ PREC_FP64, PREC_TF32, PREC_3XTF32, PREC_TF32_MMA, PREC_3XTF32_MMA, PREC_FP64_COL
 PRECISIONS = {"fp64": PREC_FP64, "tf32": PREC_TF32, "3xtf32": PREC_3XTF32,
               "tf32-mma": PREC_TF32_MMA, "3xtf32-mma": PREC_3XTF32_MMA, "fp64-collapsed": PREC_FP64_COLLAPSED}
 MAX_PCT = 16
+ABI_VERSION = 2
 
 EXPORTS = ("bisip_abi_version", "bisip_last_error", "bisip_launch_count", "bisip_forward",
            "bisip_log_probability", "bisip_decomp_build_kernel", "bisip_n_keep",
            "bisip_ensemble_run", "bisip_column_stats_workspace", "bisip_column_stats",
-           "bisip_decomp_kernel_kind")
+           "bisip_decomp_kernel_kind", "bisip_model_percentile")
 KERNEL_KINDS = {0: "dmma", 1: "dmma-cluster", 2: "mma-tf32", 3: "tcgen05", 4: "tcgen05-cluster", 5: "fp64-collapsed"}
 
 
@@ -73,7 +74,10 @@ def load():
     lib.bisip_column_stats.restype = C.c_int
     lib.bisip_column_stats.argtypes = [vp, i32, i64, i32, i32, C.POINTER(C.c_int64), C.POINTER(C.c_double),
                                        vp, vp, vp, vp, i64, vp]
-    if lib.bisip_abi_version() != 1:
+    lib.bisip_model_percentile.restype = C.c_int
+    lib.bisip_model_percentile.argtypes = [C.POINTER(ModelDesc), i32, i64, vp, vp, i64, vp, vp, i64, i32,
+                                           C.POINTER(C.c_int64), C.POINTER(C.c_double), vp, vp]
+    if lib.bisip_abi_version() != ABI_VERSION:
         raise BisipError("libbisip_b200.so ABI version mismatch")
     _lib = lib
     return lib

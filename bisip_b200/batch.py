@@ -148,7 +148,8 @@ class BatchInversion:
 
     def max_batch(self, n_keep, keep_chain):
         free, _ = torch.cuda.mem_get_info(self.device)
-        per = n_keep * self.nwalkers * (self.ndim + 1) * 8 * 2 + self.nwalkers * self.ndim * 8 * 4 + 4096
+        # kept chain (+ log-prob when the chain is kept); the statistics read it in place: no workspace
+        per = n_keep * self.nwalkers * (self.ndim + (1 if keep_chain else 0)) * 8 + self.nwalkers * self.ndim * 8 * 4 + 4096
         return max(1, min(65535, int(0.7 * free // per)))
 
     # ------------------------------------------------------------------ fit

@@ -1,4 +1,6 @@
-// extern "C" boundary of libbisip_b200.so — see include/bisip_b200.h for the contract.
+// extern "C" boundary of libbisip_b200.so — see include/bisip_b200.h for the contract.  The kernels are launched by
+// the per-family translation units (ens_*.cu, batch_*.cu; declared in launch.cuh); this file validates arguments,
+// plans the launch and holds the statistics entry points.
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -6,30 +8,26 @@
 #include <cmath>
 #include <string>
 
-#include "common.cuh"
-#include "decomp_eval.cuh"
-#include "models.cuh"
-#include "sampler.cuh"
+#include "launch.cuh"
 #include "stats.cuh"
+#include "model_pct.cuh"
 
-using namespace bisip;
+namespace bisip {
 
-namespace {
-
-thread_local std::string g_err;
-std::atomic<long long> g_launches{0};
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
 
 int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
 }
+void count_launches(int n) { g_launches.fetch_add(n); }
 
-#define BISIP_CUDA(expr)                                                                      \
-  do {                                                                                        \
-    cudaError_t e_ = (expr);                                                                  \
-    if (e_ != cudaSuccess)                                                                    \
-      return fail(BISIP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));        \
-  } while (0)
+}  // namespace bisip
+
+using namespace bisip;
+
+namespace {
 
 // The kernels must run on the device that owns the caller's buffers, whatever device is current in the calling
 // thread (one host thread may drive several GPUs): the entry points switch to the device of their primary pointer
@@ -77,451 +75,6 @@ int check_desc(const bisip_model_desc* d) {
   return BISIP_OK;
 }
 
-int device_smem_optin() {
-  int dev = 0, v = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-  cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  return v;
-}
-
-// ------------------------------------------------------------------------------------------
-// Batched forward / log-probability kernels (same evaluators as the sampler).
-// grid (chunks, B): CTA (c, b) handles theta rows [c*kRows, ...) of spectrum b, striding by gridDim.x.
-constexpr int kRows = 128;
-
-// Vector-model ensemble kernels: CTA size and resident CTAs per SM.  Their evaluation phase is short, so
-// the serial phases of the stretch move (proposals, accept, split) are about half of a step: many co-resident
-// spectra hide them, and for <= 128 walkers 128-thread CTAs (8 or 6 per SM instead of 4 x 256) keep fewer
-// lanes idle in those phases.  Values from the sweeps in profiles/r01c_vec_occupancy.md and
-// profiles/r01d_vec_kernels.md (W=128, N=64).
-#ifdef BISIP_VEC_MINB
-constexpr int kMinBVec = BISIP_VEC_MINB;
-#else
-constexpr int kMinBVec = 4;      // 256-thread CTAs, 64 registers
-#endif
-constexpr int kVecSmallW = 128;  // walkers up to which the 128-thread variant is used
-#ifdef BISIP_COLLAPSED_MINB
-constexpr int kMinBCollapsed = BISIP_COLLAPSED_MINB;
-#else
-constexpr int kMinBCollapsed = 3;   // collapsed decomposition, 256-thread CTAs: 80 registers and no spills; at 4 per SM
-                                    // (64 registers) the spill reloads cost more than the fourth CTA hides (-4 %)
-#endif
-
-// launch ensemble_kernel<VecEvaluator<Row>> in the shape picked for W walkers; MB128 = CTAs/SM of the
-// 128-thread variant (8 -> 64 registers, 6 -> 80 registers)
-template <class Row, int MB128>
-int launch_vec_ensemble(const EnsembleParams& P, dim3 grid, size_t smem, cudaStream_t st, const char* name);
-
-struct BatchParams {
-  bisip_model_desc d;
-  int B, n_theta;
-  const double* theta;
-  const double* w; long long w_stride;
-  const double* taus; const double* log_taus; long long tau_stride;
-  const double* y; const double* yerr; const double* bounds;
-  double* Z; double* lp;
-};
-
-template <int KC, bool WANT_Z>
-__global__ void __launch_bounds__(kThreads) decomp_batch_kernel(const BatchParams P) {
-  extern __shared__ __align__(16) double smem[];
-  const int b = blockIdx.y, ndim = P.d.ndim, N = P.d.n_freq;
-  DecompShape sh(P.d.n_freq, P.d.n_tau, P.d.n_coef);
-  DecompSmem s;
-  double* p = decomp_carve(s, smem, sh, kRows);
-  double* prop = p; p += kRows * ndim;
-  double* chi = p; p += kRows;
-  double* bnd = p; p += 2 * ndim;
-  double* red = p;
-  if (!WANT_Z) for (int i = threadIdx.x; i < 2 * ndim; i += kThreads) bnd[i] = P.bounds[i];
-  decomp_init(s, sh, P.d.c_exp, P.w + (size_t)b * P.w_stride, P.taus + (size_t)b * P.tau_stride,
-              P.log_taus + (size_t)b * P.tau_stride * P.d.n_coef,
-              WANT_Z ? nullptr : P.y + (size_t)b * 2 * N, WANT_Z ? nullptr : P.yerr + (size_t)b * 2 * N, red);
-  for (int r0 = blockIdx.x * kRows; r0 < P.n_theta; r0 += gridDim.x * kRows) {
-    const int n = min(kRows, P.n_theta - r0);
-    const double* th = P.theta + ((size_t)b * P.n_theta + r0) * ndim;
-    for (int i = threadIdx.x; i < kRows * ndim; i += kThreads) prop[i] = (i < n * ndim) ? th[i] : 0.0;
-    __syncthreads();
-    if (WANT_Z) {
-      decomp_eval_Z<KC>(s, sh, prop, ndim, n, P.Z + ((size_t)b * P.n_theta + r0) * 2 * N);
-    } else {
-      NoSide ns;
-      decomp_eval_chi<KC>(s, sh, prop, ndim, n, kRows, chi, ns);
-      __syncthreads();
-      for (int q = threadIdx.x; q < n; q += kThreads)
-        P.lp[(size_t)b * P.n_theta + r0 + q] =
-            in_bounds(prop + q * ndim, bnd, ndim) ? -0.5 * (chi[q] + s.llconst) : neg_inf();
-    }
-    __syncthreads();
-  }
-}
-
-// Collapsed decomposition (decomp_collapsed.cuh): same grid as decomp_batch_kernel.
-template <bool WANT_Z>
-__global__ void __launch_bounds__(kThreads) decomp_c_batch_kernel(const BatchParams P) {
-  extern __shared__ __align__(16) double smem[];
-  const int b = blockIdx.y, ndim = P.d.ndim, N = P.d.n_freq;
-  DecompCShape sh(P.d.n_freq, P.d.n_tau, P.d.n_coef);
-  DecompCSmem s;
-  double* p = decomp_c_carve(s, smem, sh, kRows);
-  double* prop = p; p += kRows * ndim;
-  double* chi = p; p += kRows;
-  double* bnd = p; p += 2 * ndim;
-  double* red = p;
-  if (!WANT_Z) for (int i = threadIdx.x; i < 2 * ndim; i += kThreads) bnd[i] = P.bounds[i];
-  decomp_c_init(s, sh, P.d.c_exp, P.w + (size_t)b * P.w_stride, P.taus + (size_t)b * P.tau_stride,
-                P.log_taus + (size_t)b * P.tau_stride * P.d.n_coef,
-                WANT_Z ? nullptr : P.y + (size_t)b * 2 * N, WANT_Z ? nullptr : P.yerr + (size_t)b * 2 * N, red);
-  for (int r0 = blockIdx.x * kRows; r0 < P.n_theta; r0 += gridDim.x * kRows) {
-    const int n = min(kRows, P.n_theta - r0);
-    const double* th = P.theta + ((size_t)b * P.n_theta + r0) * ndim;
-    for (int i = threadIdx.x; i < kRows * ndim; i += kThreads) prop[i] = (i < n * ndim) ? th[i] : 0.0;
-    __syncthreads();
-    if (WANT_Z) {
-      decomp_c_eval_Z(s, sh, prop, ndim, n, P.Z + ((size_t)b * P.n_theta + r0) * 2 * N);
-    } else {
-      decomp_c_eval_chi(s, sh, prop, ndim, n, kRows, chi);
-      __syncthreads();
-      for (int q = threadIdx.x; q < n; q += kThreads)
-        P.lp[(size_t)b * P.n_theta + r0 + q] =
-            in_bounds(prop + q * ndim, bnd, ndim) ? -0.5 * (chi[q] + s.llconst) : neg_inf();
-    }
-    __syncthreads();
-  }
-}
-
-template <class Row, bool WANT_Z>
-__global__ void __launch_bounds__(kThreads) vec_batch_kernel(const BatchParams P) {
-  extern __shared__ __align__(16) double smem[];
-  const int b = blockIdx.y, ndim = P.d.ndim, N = P.d.n_freq;
-  VecSmem s;
-  double* p = vec_carve(s, smem, N, kRows, Row::kRC);
-  double* prop = p; p += kRows * ndim;
-  double* chi = p; p += kRows;
-  double* bnd = p; p += 2 * ndim;
-  double* red = p;
-  if (!WANT_Z) for (int i = threadIdx.x; i < 2 * ndim; i += kThreads) bnd[i] = P.bounds[i];
-  vec_init(s, N, P.w + (size_t)b * P.w_stride, WANT_Z ? nullptr : P.y + (size_t)b * 2 * N,
-           WANT_Z ? nullptr : P.yerr + (size_t)b * 2 * N, red);
-  for (int r0 = blockIdx.x * kRows; r0 < P.n_theta; r0 += gridDim.x * kRows) {
-    const int n = min(kRows, P.n_theta - r0);
-    const double* th = P.theta + ((size_t)b * P.n_theta + r0) * ndim;
-    for (int i = threadIdx.x; i < kRows * ndim; i += kThreads) prop[i] = (i < n * ndim) ? th[i] : 0.0;
-    __syncthreads();
-    vec_prepare_rows<Row>(s, P.d.n_modes, prop, ndim, n);
-    __syncthreads();
-    if (WANT_Z) {
-      vec_eval_Z<Row>(s, N, P.d.n_modes, n, P.Z + ((size_t)b * P.n_theta + r0) * 2 * N);
-    } else {
-      vec_eval_chi<Row>(s, N, P.d.n_modes, n, chi);
-      __syncthreads();
-      for (int q = threadIdx.x; q < n; q += kThreads)
-        P.lp[(size_t)b * P.n_theta + r0 + q] =
-            in_bounds(prop + q * ndim, bnd, ndim) ? -0.5 * (chi[q] + s.llconst) : neg_inf();
-    }
-    __syncthreads();
-  }
-}
-
-// per-proposal constants of the vector-model kernel that check_desc()/run_batch() will pick
-int vec_row_consts(const bisip_model_desc& d) {
-  switch (d.model) {
-    case BISIP_MODEL_DIAS: return DiasRow::kRC;
-    case BISIP_MODEL_SHIN: return ShinRow::kRC;
-    default:
-      switch (d.n_modes) {
-        case 1: return ColeColeRowT<1>::kRC;
-        case 2: return ColeColeRowT<2>::kRC;
-        case 3: return ColeColeRowT<3>::kRC;
-        case 4: return ColeColeRowT<4>::kRC;
-        default: return ColeColeRow::kRC;
-      }
-  }
-}
-
-size_t batch_smem_bytes(const bisip_model_desc& d) {
-  size_t dbl = (size_t)kRows * d.ndim + kRows + 2 * d.ndim + kWarps;
-  if (d.model == BISIP_MODEL_DECOMP)
-    dbl += decomp_smem_doubles(DecompShape(d.n_freq, d.n_tau, d.n_coef), kRows);
-  else
-    dbl += vec_smem_doubles(d.n_freq, kRows, vec_row_consts(d));
-  return dbl * 8;
-}
-
-template <typename K>
-int launch(K kernel, dim3 grid, size_t smem, cudaStream_t st, const char* name, const void* params_ptr,
-           int threads = kThreads) {
-  if ((int)smem > device_smem_optin())
-    return fail(BISIP_ERR_UNSUPPORTED, std::string(name) + ": problem does not fit in shared memory");
-  BISIP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  void* args[] = {const_cast<void*>(params_ptr)};
-  BISIP_CUDA(cudaLaunchKernel((const void*)kernel, grid, dim3(threads), args, smem, st));
-  g_launches.fetch_add(1);
-  return BISIP_OK;
-}
-
-template <class Row, int MB128>
-int launch_vec_ensemble(const EnsembleParams& P, dim3 grid, size_t smem, cudaStream_t st, const char* name) {
-  if (P.W <= kVecSmallW)
-    return launch(ensemble_kernel<VecEvaluator<Row>, MB128, 128>, grid, smem, st, name, &P, 128);
-  return launch(ensemble_kernel<VecEvaluator<Row>, kMinBVec, kThreads>, grid, smem, st, name, &P, kThreads);
-}
-
-template <typename K>
-int launch_cluster(K kernel, dim3 grid, int cluster, size_t smem, cudaStream_t st, const char* name,
-                   const void* params_ptr) {
-  if ((int)smem > device_smem_optin())
-    return fail(BISIP_ERR_UNSUPPORTED, std::string(name) + ": problem does not fit in shared memory");
-  BISIP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  void* args[] = {const_cast<void*>(params_ptr)};
-  BISIP_CUDA(cudaLaunchKernelExC(&cfg, (const void*)kernel, args));
-  g_launches.fetch_add(1);
-  return BISIP_OK;
-}
-
-// Large tau grids: pick the cluster size (column split) so that K fits; prefer two CTAs per SM.
-struct RcPlan { int cs; bool two_per_sm; size_t smem; };
-// 0 = FP64, 1 = TF32, 3 = 3xTF32 (operand planes per product)
-int prec_planes(int precision) {
-  switch (precision) {
-    case BISIP_PREC_TF32: case BISIP_PREC_TF32_MMA: return 1;
-    case BISIP_PREC_3XTF32: case BISIP_PREC_3XTF32_MMA: return 3;
-    default: return 0;
-  }
-}
-size_t rc_eval_doubles(const bisip_model_desc& d, int rows_pad, int cs) {
-  switch (prec_planes(d.precision)) {
-    case 1: return DecompTF32Evaluator<1>::smem_doubles(d, rows_pad, cs);
-    case 3: return DecompTF32Evaluator<3>::smem_doubles(d, rows_pad, cs);
-    default: return DecompRCEvaluator::smem_doubles(d, rows_pad, cs);
-  }
-}
-int plan_rc(const bisip_model_desc& d, size_t other_bytes, int rows_pad, RcPlan* out) {
-  // Smallest cluster first; for a given cluster size two CTAs per SM if they fit, else one.  A wider cluster is
-  // worse than a lower occupancy: every CTA of a cluster repeats the sampler's serial phases, and measured on
-  // B200 (W=256, N=64) a 2-CTA cluster at one CTA/SM runs n_tau=256 at 24.7 TFLOP/s while 4-CTA clusters at two
-  // CTAs/SM reach 20.6-22.0 TFLOP/s for n_tau=160..240 (profiles/r01e_cluster_plan.md).
-  const size_t two = 113 * 1024, one = (size_t)device_smem_optin();
-  const int cands[3] = {1, 2, 4};
-  for (int i = 0; i < 3; ++i) {
-    const size_t smem = other_bytes + rc_eval_doubles(d, rows_pad, cands[i]) * 8;
-    if (smem <= two) { *out = {cands[i], true, smem}; return BISIP_OK; }
-    if (smem <= one) { *out = {cands[i], false, smem}; return BISIP_OK; }
-  }
-  return fail(BISIP_ERR_UNSUPPORTED, "Decomp: n_tau x n_freq too large for a 4-CTA cluster's shared memory");
-}
-// the clustered ("rc") layout serves every mma.sync reduced-precision run and every FP64 run with n_tau > 64
-bool use_rc(const bisip_model_desc& d) {
-  return d.model == BISIP_MODEL_DECOMP && d.precision != BISIP_PREC_FP64_COLLAPSED &&
-         (d.n_tau > 64 || d.precision != BISIP_PREC_FP64);
-}
-
-// tcgen05 path (decomp_umma.cuh): BISIP_PREC_TF32 / _3XTF32 whenever one M = 128 tile holds a half-step
-// (rows <= 128), 2N <= 128 columns, and the B planes fit in shared memory next to `other_bytes`.
-// n_tau <= 64: 256 tensor-memory columns per CTA, two CTAs per SM — the request is padded so that a third CTA
-// (which would spin in tcgen05.alloc) never becomes resident.  n_tau > 64: 512 columns, so the request is padded
-// past half an SM's shared memory and exactly one CTA is resident.
-struct UmmaPlan { bool ok; bool two_per_sm; size_t smem; bool cluster; };
-UmmaPlan plan_umma(const bisip_model_desc& d, size_t other_bytes, int rows, bool allow_cluster = false) {
-  UmmaPlan pl{false, false, 0, false};
-  const int planes = prec_planes(d.precision);
-  if (d.model != BISIP_MODEL_DECOMP || (d.precision != BISIP_PREC_TF32 && d.precision != BISIP_PREC_3XTF32)) return pl;
-  if (rows > kUmmaRows || !DecompUmmaShape::fits(d.n_freq, d.n_tau)) return pl;
-  const DecompUmmaShape sh(d.n_freq, d.n_tau, d.n_coef);
-  size_t smem = other_bytes + decomp_umma_smem_doubles(sh, planes) * 8;
-  if (smem > (size_t)device_smem_optin()) {
-    // K planes too large for one CTA: a 2-CTA cluster splits the real | imaginary columns (sampler kernel only)
-    if (!allow_cluster) return pl;
-    const DecompUmmaShape shc(d.n_freq, d.n_tau, d.n_coef, 1, 0);
-    smem = other_bytes + decomp_umma_smem_doubles(shc, planes) * 8;
-    if (smem > (size_t)device_smem_optin()) return pl;
-    pl.ok = true;
-    pl.cluster = true;
-    pl.smem = smem < 116 * 1024 ? 116 * 1024 : smem;      // 512 tensor-memory columns: one CTA per SM
-    return pl;
-  }
-  pl.ok = true;
-  pl.two_per_sm = sh.nchunks == 1 && smem <= 113 * 1024;
-  const size_t floor_bytes = pl.two_per_sm ? 77 * 1024 : 116 * 1024;
-  pl.smem = smem < floor_bytes ? floor_bytes : smem;
-  return pl;
-}
-
-// uniform access to the three clustered evaluators for the batch kernel
-template <int PREC> struct RcOps;
-template <> struct RcOps<0> {
-  using Smem = DecompRCSmem;
-  static __device__ double* carve(Smem& s, double* b, const DecompRCShape& sh, int rp) { return decomp_rc_carve(s, b, sh, rp); }
-  template <class... A> static __device__ void init(A&&... a) { decomp_rc_init(a...); }
-  template <class... A> static __device__ void chi(A&&... a) { decomp_rc_eval_chi(a...); }
-  template <class... A> static __device__ void Z(A&&... a) { decomp_rc_eval_Z(a...); }
-};
-template <> struct RcOps<1> {
-  using Smem = DecompTF32Smem;
-  static __device__ double* carve(Smem& s, double* b, const DecompRCShape& sh, int rp) { return decomp_tf32_carve<1>(s, b, sh, rp); }
-  template <class... A> static __device__ void init(A&&... a) { decomp_tf32_init<1>(a...); }
-  template <class... A> static __device__ void chi(A&&... a) { decomp_tf32_eval_chi<1>(a...); }
-  template <class... A> static __device__ void Z(A&&... a) { decomp_tf32_eval_Z<1>(a...); }
-};
-template <> struct RcOps<3> {
-  using Smem = DecompTF32Smem;
-  static __device__ double* carve(Smem& s, double* b, const DecompRCShape& sh, int rp) { return decomp_tf32_carve<3>(s, b, sh, rp); }
-  template <class... A> static __device__ void init(A&&... a) { decomp_tf32_init<3>(a...); }
-  template <class... A> static __device__ void chi(A&&... a) { decomp_tf32_eval_chi<3>(a...); }
-  template <class... A> static __device__ void Z(A&&... a) { decomp_tf32_eval_Z<3>(a...); }
-};
-
-// Batched forward / log-probability for large tau grids: grid (chunks*CS, B), cluster (CS,1,1).
-template <int PREC, bool WANT_Z>
-__global__ void __launch_bounds__(kThreads) decomp_rc_batch_kernel(const BatchParams P) {
-  using Ops = RcOps<PREC>;
-  extern __shared__ __align__(16) double smem[];
-  cg::cluster_group cluster = cg::this_cluster();
-  const int cs = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
-  const int b = blockIdx.y, ndim = P.d.ndim, N = P.d.n_freq;
-  const int chunk0 = blockIdx.x / cs, nchunks = gridDim.x / cs;
-  DecompRCShape sh(P.d.n_freq, P.d.n_tau, P.d.n_coef, cs, crank);
-  typename Ops::Smem s;
-  double* p = Ops::carve(s, smem, sh, kRows);
-  double* prop = p; p += kRows * ndim;
-  double* chi = p; p += kRows;
-  double* bnd = p; p += 2 * ndim;
-  double* red = p;
-  if (!WANT_Z) for (int i = threadIdx.x; i < 2 * ndim; i += kThreads) bnd[i] = P.bounds[i];
-  Ops::init(s, sh, P.d.c_exp, P.w + (size_t)b * P.w_stride, P.taus + (size_t)b * P.tau_stride,
-                 P.log_taus + (size_t)b * P.tau_stride * P.d.n_coef,
-                 WANT_Z ? nullptr : P.y + (size_t)b * 2 * N, WANT_Z ? nullptr : P.yerr + (size_t)b * 2 * N, red);
-  for (int r0 = chunk0 * kRows; r0 < P.n_theta; r0 += nchunks * kRows) {
-    const int n = min(kRows, P.n_theta - r0);
-    const double* th = P.theta + ((size_t)b * P.n_theta + r0) * ndim;
-    for (int i = threadIdx.x; i < kRows * ndim; i += kThreads) prop[i] = (i < n * ndim) ? th[i] : 0.0;
-    __syncthreads();
-    if (WANT_Z) {
-      Ops::Z(s, sh, prop, ndim, n, P.Z + ((size_t)b * P.n_theta + r0) * 2 * N);
-    } else {
-      const int rows_cap = kRows;
-      Ops::chi(s, sh, prop, ndim, n, rows_cap, chi);
-      __syncthreads();
-      if (crank == 0)
-        for (int q = threadIdx.x; q < n; q += kThreads)
-          P.lp[(size_t)b * P.n_theta + r0 + q] =
-              in_bounds(prop + q * ndim, bnd, ndim) ? -0.5 * (chi[q] + s.llconst) : neg_inf();
-    }
-    __syncthreads();
-  }
-  if (cs > 1) cluster.sync();
-}
-
-// Batched forward / log-probability on the tcgen05 path: grid (chunks, B), 128 theta rows per tile.
-template <int PREC, bool WANT_Z>
-__global__ void __launch_bounds__(kThreads) decomp_umma_batch_kernel(const BatchParams P) {
-  extern __shared__ __align__(16) double smem[];
-  const int b = blockIdx.y, ndim = P.d.ndim, N = P.d.n_freq;
-  DecompUmmaShape sh(P.d.n_freq, P.d.n_tau, P.d.n_coef);
-  DecompUmmaSmem s;
-  double* p = decomp_umma_carve<PREC>(s, smem, sh);
-  double* prop = p; p += kRows * ndim;
-  double* chi = p; p += kRows;
-  double* bnd = p; p += 2 * ndim;
-  double* red = p;
-  if (!WANT_Z) for (int i = threadIdx.x; i < 2 * ndim; i += kThreads) bnd[i] = P.bounds[i];
-  decomp_umma_init<PREC>(s, sh, P.d.c_exp, P.w + (size_t)b * P.w_stride, P.taus + (size_t)b * P.tau_stride,
-                         P.log_taus + (size_t)b * P.tau_stride * P.d.n_coef,
-                         WANT_Z ? nullptr : P.y + (size_t)b * 2 * N, WANT_Z ? nullptr : P.yerr + (size_t)b * 2 * N, red);
-  for (int r0 = blockIdx.x * kRows; r0 < P.n_theta; r0 += gridDim.x * kRows) {
-    const int n = min(kRows, P.n_theta - r0);
-    const double* th = P.theta + ((size_t)b * P.n_theta + r0) * ndim;
-    for (int i = threadIdx.x; i < kRows * ndim; i += kThreads) prop[i] = (i < n * ndim) ? th[i] : 0.0;
-    __syncthreads();
-    decomp_umma_eval<PREC, WANT_Z>(s, sh, prop, ndim, n, chi,
-                                   WANT_Z ? P.Z + ((size_t)b * P.n_theta + r0) * 2 * N : nullptr);
-    __syncthreads();
-    if (!WANT_Z)
-      for (int q = threadIdx.x; q < n; q += kThreads)
-        P.lp[(size_t)b * P.n_theta + r0 + q] =
-            in_bounds(prop + q * ndim, bnd, ndim) ? -0.5 * (chi[q] + s.llconst) : neg_inf();
-    __syncthreads();
-  }
-  decomp_umma_release(s, sh);
-}
-
-template <bool WANT_Z>
-int run_batch(const BatchParams& P, cudaStream_t st) {
-  {
-    const size_t other = ((size_t)kRows * P.d.ndim + kRows + 2 * P.d.ndim + kWarps) * 8;
-    const UmmaPlan up = plan_umma(P.d, other, kRows);
-    if (up.ok) {
-      int chunks = ceil_div(P.n_theta, kRows);
-      const int cap = max(1, (148 * 2) / max(1, P.B));
-      if (chunks > cap) chunks = cap;
-      const dim3 g(chunks, P.B);
-      if (prec_planes(P.d.precision) == 3)
-        return launch(decomp_umma_batch_kernel<3, WANT_Z>, g, up.smem, st, "decomp_umma_3xtf32_batch", &P);
-      return launch(decomp_umma_batch_kernel<1, WANT_Z>, g, up.smem, st, "decomp_umma_tf32_batch", &P);
-    }
-  }
-  if (P.d.model == BISIP_MODEL_DECOMP && P.d.precision == BISIP_PREC_FP64_COLLAPSED) {
-    const size_t smem = (((size_t)kRows * P.d.ndim + kRows + 2 * P.d.ndim + kWarps) +
-                         decomp_c_smem_doubles(DecompCShape(P.d.n_freq, P.d.n_tau, P.d.n_coef), kRows)) * 8;
-    int chunks = ceil_div(P.n_theta, kRows);
-    const int cap = max(1, (148 * 4) / max(1, P.B));
-    if (chunks > cap) chunks = cap;
-    return launch(decomp_c_batch_kernel<WANT_Z>, dim3(chunks, P.B), smem, st, "decomp_collapsed_batch", &P);
-  }
-  if (use_rc(P.d)) {
-    RcPlan plan;
-    const size_t other = ((size_t)kRows * P.d.ndim + kRows + 2 * P.d.ndim + kWarps) * 8;
-    if (int rc = plan_rc(P.d, other, kRows, &plan)) return rc;
-    int chunks = ceil_div(P.n_theta, kRows);
-    const int cap = max(1, (148 * 2) / max(1, P.B * plan.cs));
-    if (chunks > cap) chunks = cap;
-    const dim3 g(chunks * plan.cs, P.B);
-    switch (prec_planes(P.d.precision)) {
-      case 1: return launch_cluster(decomp_rc_batch_kernel<1, WANT_Z>, g, plan.cs, plan.smem, st, "decomp_tf32_batch", &P);
-      case 3: return launch_cluster(decomp_rc_batch_kernel<3, WANT_Z>, g, plan.cs, plan.smem, st, "decomp_3xtf32_batch", &P);
-      default: return launch_cluster(decomp_rc_batch_kernel<0, WANT_Z>, g, plan.cs, plan.smem, st, "decomp_rc_batch", &P);
-    }
-  }
-  const size_t smem = batch_smem_bytes(P.d);
-  int chunks = ceil_div(P.n_theta, kRows);
-  const int cap = max(1, (148 * 8) / max(1, P.B));   // enough CTAs to fill the chip, no more
-  if (chunks > cap) chunks = cap;
-  dim3 grid(chunks, P.B);
-  switch (P.d.model) {
-    case BISIP_MODEL_COLECOLE:
-      switch (P.d.n_modes) {
-        case 1: return launch(vec_batch_kernel<ColeColeRowT<1>, WANT_Z>, grid, smem, st, "colecole_batch", &P);
-        case 2: return launch(vec_batch_kernel<ColeColeRowT<2>, WANT_Z>, grid, smem, st, "colecole_batch", &P);
-        case 3: return launch(vec_batch_kernel<ColeColeRowT<3>, WANT_Z>, grid, smem, st, "colecole_batch", &P);
-        case 4: return launch(vec_batch_kernel<ColeColeRowT<4>, WANT_Z>, grid, smem, st, "colecole_batch", &P);
-        default: return launch(vec_batch_kernel<ColeColeRow, WANT_Z>, grid, smem, st, "colecole_batch", &P);
-      }
-    case BISIP_MODEL_DIAS: return launch(vec_batch_kernel<DiasRow, WANT_Z>, grid, smem, st, "dias_batch", &P);
-    case BISIP_MODEL_SHIN: return launch(vec_batch_kernel<ShinRow, WANT_Z>, grid, smem, st, "shin_batch", &P);
-    default: {
-      const int KC = ceil_div(P.d.n_tau, 16);
-      switch (KC) {
-        case 1: return launch(decomp_batch_kernel<1, WANT_Z>, grid, smem, st, "decomp_batch", &P);
-        case 2: return launch(decomp_batch_kernel<2, WANT_Z>, grid, smem, st, "decomp_batch", &P);
-        case 3: return launch(decomp_batch_kernel<3, WANT_Z>, grid, smem, st, "decomp_batch", &P);
-        default: return launch(decomp_batch_kernel<4, WANT_Z>, grid, smem, st, "decomp_batch", &P);
-      }
-    }
-  }
-}
-
 __global__ void build_kernel_matrix(const double* w, int N, const double* taus, int S, double c_exp, double* K) {
   double cs, sn;
   sincospi(0.5 * c_exp, &sn, &cs);
@@ -539,8 +92,8 @@ __global__ void build_kernel_matrix(const double* w, int N, const double* taus, 
 extern "C" {
 
 int bisip_abi_version(void) { return BISIP_ABI_VERSION; }
-const char* bisip_last_error(void) { return g_err.c_str(); }
-int64_t bisip_launch_count(void) { return g_launches.load(); }
+const char* bisip_last_error(void) { return bisip::g_err.c_str(); }
+int64_t bisip_launch_count(void) { return bisip::g_launches.load(); }
 
 int bisip_decomp_kernel_kind(const bisip_model_desc* desc, int n_walkers) {
   if (int rc = check_desc(desc)) return rc;
@@ -572,7 +125,8 @@ int bisip_forward(const bisip_model_desc* desc, int n_spectra, int n_theta, cons
   if (n_spectra > 65535) return fail(BISIP_ERR_UNSUPPORTED, "bisip_forward: n_spectra > 65535 per call");
   DeviceGuard guard(theta);
   BatchParams P{*desc, n_spectra, n_theta, theta, w, w_stride, taus, log_taus, tau_stride, nullptr, nullptr, nullptr, Z, nullptr};
-  return run_batch<true>(P, (cudaStream_t)stream);
+  return desc->model == BISIP_MODEL_DECOMP ? run_batch_decomp(P, true, (cudaStream_t)stream)
+                                           : run_batch_vec(P, true, (cudaStream_t)stream);
 }
 
 int bisip_log_probability(const bisip_model_desc* desc, int n_spectra, int n_theta, const double* theta,
@@ -586,7 +140,8 @@ int bisip_log_probability(const bisip_model_desc* desc, int n_spectra, int n_the
   if (n_spectra > 65535) return fail(BISIP_ERR_UNSUPPORTED, "bisip_log_probability: n_spectra > 65535 per call");
   DeviceGuard guard(theta);
   BatchParams P{*desc, n_spectra, n_theta, theta, w, w_stride, taus, log_taus, tau_stride, y, yerr, bounds, nullptr, lp_out};
-  return run_batch<false>(P, (cudaStream_t)stream);
+  return desc->model == BISIP_MODEL_DECOMP ? run_batch_decomp(P, false, (cudaStream_t)stream)
+                                           : run_batch_vec(P, false, (cudaStream_t)stream);
 }
 
 int bisip_decomp_build_kernel(const double* w, int n_freq, const double* taus, int n_tau, double c_exp, double* K,
@@ -595,7 +150,7 @@ int bisip_decomp_build_kernel(const double* w, int n_freq, const double* taus, i
   DeviceGuard guard(K);
   build_kernel_matrix<<<ceil_div(n_freq * n_tau, 256), 256, 0, (cudaStream_t)stream>>>(w, n_freq, taus, n_tau, c_exp, K);
   BISIP_CUDA(cudaGetLastError());
-  g_launches.fetch_add(1);
+  count_launches(1);
   return BISIP_OK;
 }
 
@@ -638,106 +193,107 @@ int bisip_ensemble_run(const bisip_model_desc* desc, int n_spectra, int n_walker
   switch (desc->model) {
     case BISIP_MODEL_COLECOLE:
       smem += vec_smem_doubles(desc->n_freq, rp, vec_row_consts(*desc)) * 8;
-      switch (desc->n_modes) {
-        case 1: return launch_vec_ensemble<ColeColeRowT<1>, 8>(P, grid, smem, st, "ensemble_colecole");
-        case 2: return launch_vec_ensemble<ColeColeRowT<2>, 6>(P, grid, smem, st, "ensemble_colecole");
-        case 3: return launch(ensemble_kernel<VecEvaluator<ColeColeRowT<3>>, 2>, grid, smem, st, "ensemble_colecole", &P);
-        case 4: return launch(ensemble_kernel<VecEvaluator<ColeColeRowT<4>>, 1>, grid, smem, st, "ensemble_colecole", &P);
-        default: return launch(ensemble_kernel<VecEvaluator<ColeColeRow>, 1>, grid, smem, st, "ensemble_colecole", &P);
-      }
+      return launch_ens_colecole(P, grid, smem, st);
     case BISIP_MODEL_DIAS:
       smem += VecEvaluator<DiasRow>::smem_doubles(*desc, rp) * 8;
-      return launch_vec_ensemble<DiasRow, 8>(P, grid, smem, st, "ensemble_dias");
+      return launch_ens_dias_shin(P, grid, smem, st);
     case BISIP_MODEL_SHIN:
       smem += VecEvaluator<ShinRow>::smem_doubles(*desc, rp) * 8;
-      return launch_vec_ensemble<ShinRow, 6>(P, grid, smem, st, "ensemble_shin");
+      return launch_ens_dias_shin(P, grid, smem, st);
     default: {
       if (desc->precision == BISIP_PREC_FP64_COLLAPSED) {
         smem += DecompCollapsedEvaluator::smem_doubles(*desc, rp) * 8;
-        // measured (profiles/r01h_collapsed_sweep.log): 32 walkers 4.6e9 evals/s at 8 CTAs/SM vs 4.1e9 at 6;
-        // 128 walkers 8.1e9 at 6 (80 registers, no spills) vs 6.7e9 at 8
-        if (n_walkers <= 64)
-          return launch(ensemble_kernel<DecompCollapsedEvaluator, 8, 128>, grid, smem, st, "ensemble_decomp_collapsed", &P, 128);
-        if (n_walkers <= kVecSmallW)
-          return launch(ensemble_kernel<DecompCollapsedEvaluator, 6, 128>, grid, smem, st, "ensemble_decomp_collapsed", &P, 128);
-        return launch(ensemble_kernel<DecompCollapsedEvaluator, kMinBCollapsed, kThreads>, grid, smem, st,
-                      "ensemble_decomp_collapsed", &P, kThreads);
+        return launch_ens_collapsed(P, grid, smem, st);
       }
       {
         const UmmaPlan up = plan_umma(*desc, smem, (n_walkers + 1) / 2, true);
         if (up.ok && up.cluster) {
           if ((long long)n_spectra * 2 > 2147483647LL) return fail(BISIP_ERR_UNSUPPORTED, "too many spectra per call");
-          const dim3 g(n_spectra * 2);
-          return prec_planes(desc->precision) == 3
-                     ? launch_cluster(ensemble_kernel<DecompUmmaEvaluator<3, true>, 1>, g, 2, up.smem, st, "ensemble_decomp_umma_3xtf32_cluster", &P)
-                     : launch_cluster(ensemble_kernel<DecompUmmaEvaluator<1, true>, 1>, g, 2, up.smem, st, "ensemble_decomp_umma_tf32_cluster", &P);
+          return launch_ens_umma(P, dim3(n_spectra * 2), up, st);
         }
-        if (up.ok) {
-          const bool x3 = prec_planes(desc->precision) == 3;
-          if (up.two_per_sm)
-            return x3 ? launch(ensemble_kernel<DecompUmmaEvaluator<3>, 2>, grid, up.smem, st, "ensemble_decomp_umma_3xtf32", &P)
-                      : launch(ensemble_kernel<DecompUmmaEvaluator<1>, 2>, grid, up.smem, st, "ensemble_decomp_umma_tf32", &P);
-          return x3 ? launch(ensemble_kernel<DecompUmmaEvaluator<3>, 1>, grid, up.smem, st, "ensemble_decomp_umma_3xtf32", &P)
-                    : launch(ensemble_kernel<DecompUmmaEvaluator<1>, 1>, grid, up.smem, st, "ensemble_decomp_umma_tf32", &P);
-        }
+        if (up.ok) return launch_ens_umma(P, grid, up, st);
       }
       if (use_rc(*desc)) {
         RcPlan plan;
         if (int rc = plan_rc(*desc, smem, rp, &plan)) return rc;
         if ((long long)n_spectra * plan.cs > 2147483647LL) return fail(BISIP_ERR_UNSUPPORTED, "too many spectra per call");
-        dim3 g(n_spectra * plan.cs);
-#define BISIP_RC_LAUNCH(EVAL, NAME)                                                                       \
-  return plan.two_per_sm ? launch_cluster(ensemble_kernel<EVAL, 2>, g, plan.cs, plan.smem, st, NAME, &P)  \
-                         : launch_cluster(ensemble_kernel<EVAL, 1>, g, plan.cs, plan.smem, st, NAME, &P)
-        switch (prec_planes(desc->precision)) {
-          case 1: BISIP_RC_LAUNCH(DecompTF32Evaluator<1>, "ensemble_decomp_tf32");
-          case 3: BISIP_RC_LAUNCH(DecompTF32Evaluator<3>, "ensemble_decomp_3xtf32");
-          default: BISIP_RC_LAUNCH(DecompRCEvaluator, "ensemble_decomp_rc");
-        }
-#undef BISIP_RC_LAUNCH
+        return launch_ens_rc(P, dim3(n_spectra * plan.cs), plan, st);
       }
       smem += DecompEvaluator<4>::smem_doubles(*desc, rp) * 8;
-      const int KC = ceil_div(desc->n_tau, 16);
-      switch (KC) {
-        case 1: return launch(ensemble_kernel<DecompEvaluator<1>, 2>, grid, smem, st, "ensemble_decomp", &P);
-        case 2: return launch(ensemble_kernel<DecompEvaluator<2>, 2>, grid, smem, st, "ensemble_decomp", &P);
-        case 3: return launch(ensemble_kernel<DecompEvaluator<3>, 2>, grid, smem, st, "ensemble_decomp", &P);
-        default: return launch(ensemble_kernel<DecompEvaluator<4>, 2>, grid, smem, st, "ensemble_decomp", &P);
-      }
+      return launch_ens_dmma(P, grid, smem, st);
     }
   }
 }
 
-int64_t bisip_column_stats_workspace(int n_spectra, int64_t n_samples, int n_cols) {
-  if (n_spectra <= 0 || n_samples <= 0 || n_cols <= 0) return 0;
-  return (int64_t)n_spectra * n_samples * n_cols * 8;
+int64_t bisip_column_stats_workspace(int, int64_t, int) { return 0; }   // ABI 1 needed a key workspace; the chain is now read in place
+
+// launch one of the shared-memory statistics kernels if (n, R) fits in one CTA's shared memory, else report "does not fit"
+static bool stats_fits_smem(int64_t n, int R, size_t* smem) {
+  *smem = stats_smem_bytes(n, R);
+  return n <= 0x7fffffff / 8 && *smem + kStatStaticSmem <= (size_t)device_smem_optin();
 }
 
 int bisip_column_stats(const double* data, int n_spectra, int64_t n_samples, int n_cols, int n_pct,
                        const int64_t* pct_lo, const double* pct_gamma, double* pct_out, double* mean_out,
-                       double* std_out, void* workspace, int64_t workspace_bytes, void* stream) {
-  if (!data || n_spectra <= 0 || n_samples <= 0 || n_cols <= 0 || n_pct < 0 || !workspace)
+                       double* std_out, void* /*workspace*/, int64_t /*workspace_bytes*/, void* stream) {
+  if (!data || n_spectra <= 0 || n_samples <= 0 || n_cols <= 0 || n_pct < 0)
     return fail(BISIP_ERR_BAD_ARG, "bisip_column_stats: bad argument");
   if (n_pct > kMaxPct) return fail(BISIP_ERR_UNSUPPORTED, "bisip_column_stats: at most 16 percentiles per call");
   if (n_pct > 0 && (!pct_lo || !pct_gamma || !pct_out)) return fail(BISIP_ERR_BAD_ARG, "bisip_column_stats: percentile arrays null");
-  if (workspace_bytes < bisip_column_stats_workspace(n_spectra, n_samples, n_cols))
-    return fail(BISIP_ERR_BAD_ARG, "bisip_column_stats: workspace too small");
   if (n_spectra > 65535) return fail(BISIP_ERR_UNSUPPORTED, "bisip_column_stats: n_spectra > 65535 per call");
   DeviceGuard guard(data);
   cudaStream_t st = (cudaStream_t)stream;
   StatsParams P;
-  P.data = data; P.keys = (unsigned long long*)workspace; P.n = n_samples; P.ncol = n_cols; P.B = n_spectra;
+  P.data = data; P.n = n_samples; P.ncol = n_cols; P.B = n_spectra;
   P.npct = n_pct;
   for (int i = 0; i < n_pct; ++i) { P.lo[i] = pct_lo[i]; P.gamma[i] = pct_gamma[i]; }
   P.pct_out = pct_out; P.mean_out = mean_out; P.std_out = std_out;
-  dim3 g1((unsigned)((n_samples + 4095) / 4096), n_spectra);
-  transpose_keys_kernel<<<g1, kThreads, 0, st>>>(P);
+  const dim3 grid(n_cols, n_spectra);
+  size_t smem = 0;
+  if (stats_fits_smem(n_samples, 2 * n_pct, &smem))
+    return launch(column_stats_smem_kernel, grid, smem, st, "column_stats", &P, kStatThreads);
+  column_stats_global_kernel<<<grid, kThreads, 0, st>>>(P);
   BISIP_CUDA(cudaGetLastError());
-  dim3 g2(n_cols, n_spectra);
-  column_select_kernel<<<g2, kThreads, 0, st>>>(P);
-  BISIP_CUDA(cudaGetLastError());
-  g_launches.fetch_add(2);
+  count_launches(1);
   return BISIP_OK;
+}
+
+int bisip_model_percentile(const bisip_model_desc* desc, int n_spectra, int64_t n_theta, const double* theta,
+                           const double* w, int64_t w_stride, const double* taus, const double* log_taus,
+                           int64_t tau_stride, int n_pct, const int64_t* pct_lo, const double* pct_gamma,
+                           double* pct_out, void* stream) {
+  if (!desc) return fail(BISIP_ERR_BAD_ARG, "desc is null");
+  bisip_model_desc d = *desc;
+  if (d.model == BISIP_MODEL_DECOMP) d.precision = BISIP_PREC_FP64_COLLAPSED;   // the column form; FP64 for every mode
+  {
+    // this kernel loops over modes / coefficients: the tile-shaped limits of the sampler kernels do not apply
+    bisip_model_desc chk = d;
+    if (chk.model == BISIP_MODEL_COLECOLE && chk.n_modes > kMaxModes) { chk.n_modes = 1; chk.ndim = 4; }
+    if (chk.model == BISIP_MODEL_DECOMP && chk.n_coef > 8) { chk.n_coef = 8; chk.ndim = 9; }
+    if (int rc = check_desc(&chk)) return rc;
+    if (d.model == BISIP_MODEL_COLECOLE && (d.n_modes < 1 || d.ndim != 1 + 3 * d.n_modes))
+      return fail(BISIP_ERR_BAD_ARG, "ColeCole ndim != 1+3*n_modes");
+    if (d.model == BISIP_MODEL_DECOMP && (d.ndim != 1 + d.n_coef || d.n_coef > kMaxCoefPct))
+      return fail(d.n_coef > kMaxCoefPct ? BISIP_ERR_UNSUPPORTED : BISIP_ERR_BAD_ARG, "bisip_model_percentile: bad n_coef");
+  }
+  if (n_spectra <= 0 || n_theta <= 0 || !theta || !w || n_pct <= 0 || !pct_lo || !pct_gamma || !pct_out)
+    return fail(BISIP_ERR_BAD_ARG, "bisip_model_percentile: bad argument");
+  if (d.model == BISIP_MODEL_DECOMP && (!taus || !log_taus)) return fail(BISIP_ERR_BAD_ARG, "bisip_model_percentile: taus/log_taus null");
+  if (n_pct > kMaxPct) return fail(BISIP_ERR_UNSUPPORTED, "bisip_model_percentile: at most 16 percentiles per call");
+  if (n_spectra > 65535) return fail(BISIP_ERR_UNSUPPORTED, "bisip_model_percentile: n_spectra > 65535 per call");
+  DeviceGuard guard(theta);
+  size_t smem = 0;
+  if (!stats_fits_smem(n_theta, 2 * n_pct, &smem))
+    return fail(BISIP_ERR_UNSUPPORTED, "bisip_model_percentile: chain too long for one CTA's shared memory "
+                                       "(use bisip_forward + bisip_column_stats)");
+  ModelPctParams P;
+  P.d = d; P.B = n_spectra; P.n = n_theta; P.theta = theta; P.w = w; P.w_stride = w_stride;
+  P.taus = taus; P.log_taus = log_taus; P.tau_stride = tau_stride;
+  P.st.data = nullptr; P.st.n = n_theta; P.st.ncol = 2 * d.n_freq; P.st.B = n_spectra; P.st.npct = n_pct;
+  for (int i = 0; i < n_pct; ++i) { P.st.lo[i] = pct_lo[i]; P.st.gamma[i] = pct_gamma[i]; }
+  P.st.pct_out = pct_out; P.st.mean_out = nullptr; P.st.std_out = nullptr;
+  return launch(model_percentile_kernel, dim3(2 * d.n_freq, n_spectra), smem, (cudaStream_t)stream, "model_percentile", &P,
+                kStatThreads);
 }
 
 }  // extern "C"

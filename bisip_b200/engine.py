@@ -141,7 +141,7 @@ def ensemble_run(spec, coords, w, y, yerr, bounds, nsteps, seed, spectrum0=0, a=
 
 def column_stats(data, p=None, want_mean=False, want_std=False):
     """data (B, n, ncol) -> dict(pct (B, len(p), ncol), mean (B, ncol), std (B, ncol)).
-    Exact NumPy-'linear' percentiles, mean and population std over axis 1."""
+    Exact NumPy-'linear' percentiles, mean and population std over axis 1; ``data`` is read in place."""
     lib = _lib.load()
     _chk_cuda_f64(data)
     B, n, ncol = data.shape
@@ -149,8 +149,6 @@ def column_stats(data, p=None, want_mean=False, want_std=False):
     out = {}
     p_arr = np.atleast_1d(np.asarray(p, dtype=np.float64)) if p is not None else np.empty(0)
     npct = int(p_arr.shape[0])
-    wbytes = int(lib.bisip_column_stats_workspace(B, n, ncol))
-    work = torch.empty((wbytes // 8,), dtype=torch.float64, device=dev)
     mean = torch.empty((B, ncol), dtype=torch.float64, device=dev) if want_mean else None
     std = torch.empty((B, ncol), dtype=torch.float64, device=dev) if want_std else None
     pct = torch.empty((B, npct, ncol), dtype=torch.float64, device=dev) if npct else None
@@ -158,21 +156,53 @@ def column_stats(data, p=None, want_mean=False, want_std=False):
     for s0 in range(0, max(npct, 1), _lib.MAX_PCT):
         pp = p_arr[s0:s0 + _lib.MAX_PCT]
         k = int(pp.shape[0])
+        whole = k == npct                      # the usual case: the kernel writes straight into the result
         if k:
             lo, gamma = _lib.percentile_indices(n, pp)
             lo_c = (C.c_int64 * k)(*[int(v) for v in lo])
             ga_c = (C.c_double * k)(*[float(v) for v in gamma])
-            part = torch.empty((B, k, ncol), dtype=torch.float64, device=dev)
+            part = pct if whole else torch.empty((B, k, ncol), dtype=torch.float64, device=dev)
         else:
             lo_c = ga_c = None
             part = None
         rc = lib.bisip_column_stats(_lib.ptr(data), B, n, ncol, k, lo_c, ga_c, _lib.ptr(part),
                                     _lib.ptr(mean if not done_stats else None),
                                     _lib.ptr(std if not done_stats else None),
-                                    _lib.ptr(work), wbytes, _lib.stream_ptr(dev))
+                                    None, 0, _lib.stream_ptr(dev))
         _lib.check(rc, "bisip_column_stats")
         done_stats = True
-        if k:
+        if k and not whole:
             pct[:, s0:s0 + k] = part
     out["pct"], out["mean"], out["std"] = pct, mean, std
+    return out
+
+
+def model_percentile(spec, theta, w, p):
+    """Percentiles of the forward model over parameter vectors, fused (``bisip_model_percentile``): theta (B, n, ndim),
+    w (N,) or (B, N), p percentiles -> (B, len(p), 2, N).  The (n, 2N) model matrix is never materialised.  Returns None
+    when n exceeds what one CTA's shared memory holds (the caller composes ``forward`` + ``column_stats``)."""
+    lib = _lib.load()
+    _chk_cuda_f64(theta, w, spec.taus, spec.log_taus)
+    B, n, ndim = theta.shape
+    N = w.shape[-1]
+    dev = theta.device
+    p_arr = np.atleast_1d(np.asarray(p, dtype=np.float64))
+    npct = int(p_arr.shape[0])
+    out = torch.empty((B, npct, 2, N), dtype=torch.float64, device=dev)
+    d = spec.desc(N)
+    for s0 in range(0, npct, _lib.MAX_PCT):
+        pp = p_arr[s0:s0 + _lib.MAX_PCT]
+        k = int(pp.shape[0])
+        lo, gamma = _lib.percentile_indices(n, pp)
+        lo_c = (C.c_int64 * k)(*[int(v) for v in lo])
+        ga_c = (C.c_double * k)(*[float(v) for v in gamma])
+        part = out if k == npct else torch.empty((B, k, 2, N), dtype=torch.float64, device=dev)
+        rc = lib.bisip_model_percentile(C.byref(d), B, n, _lib.ptr(theta), _lib.ptr(w), _w_stride(w),
+                                        _lib.ptr(spec.taus), _lib.ptr(spec.log_taus), spec.tau_stride(), k, lo_c, ga_c,
+                                        _lib.ptr(part), _lib.stream_ptr(dev))
+        if rc == -2 and "shared memory" in (lib.bisip_last_error() or b"").decode():
+            return None
+        _lib.check(rc, "bisip_model_percentile")
+        if k != npct:
+            out[:, s0:s0 + k] = part
     return out

@@ -5,9 +5,10 @@ Same method names, argument meaning, warnings and errors as the reference
 
 * ``get_param_percentile / mean / std`` -> ``bisip_column_stats`` (exact order statistics
   with NumPy's 'linear' rule, so percentiles are bit-identical to ``np.percentile``)
-* ``get_model_percentile`` -> one batched ``bisip_forward`` over the whole flat chain
-  (the reference loops ``forward`` in Python once per sample, ``utils.py:32-34``) followed
-  by ``bisip_column_stats`` over the 2N model columns.
+* ``get_model_percentile`` -> ``bisip_model_percentile``: one CTA per model column evaluates the forward
+  model for the whole flat chain into shared memory and selects there (the reference loops ``forward`` in
+  Python once per sample, ``utils.py:32-34``); chains longer than ~27,000 samples fall back to one batched
+  ``bisip_forward`` + ``bisip_column_stats``.
 """
 import warnings
 
@@ -25,10 +26,13 @@ class utils(object):
         chain = self.parse_chain(chain, **kwargs)
         dev = _lib.require_cuda(getattr(self, "device", None))
         th = _lib.dev_f64(chain, dev).reshape(1, -1, chain.shape[-1])
-        Z = engine.forward(self._spec(dev), th, _lib.dev_const(self.data['w'], dev))   # (1, n, 2, N)
-        n, N = Z.shape[1], Z.shape[3]
-        out = engine.column_stats(Z.reshape(1, n, 2 * N), p=p)["pct"][0]
-        res = out.reshape(-1, 2, N).cpu().numpy()
+        w = _lib.dev_const(self.data['w'], dev)
+        out = engine.model_percentile(self._spec(dev), th, w, p)          # fused: forward + select per model column
+        if out is None:                                                  # chain longer than a CTA's shared memory
+            Z = engine.forward(self._spec(dev), th, w)                   # (1, n, 2, N)
+            n, N = Z.shape[1], Z.shape[3]
+            out = engine.column_stats(Z.reshape(1, n, 2 * N), p=p)["pct"].reshape(1, -1, 2, N)
+        res = out[0].cpu().numpy()
         return res if np.ndim(p) else res[0]
 
     # ---------------------------------------------------------------- parameter statistics

@@ -20,6 +20,7 @@
  *                               sampler.get_chain (models.py:137)
  *   bisip_column_stats       <- np.percentile / np.mean / np.std over the flat chain
  *                               (utils.py:35, :53, :69, :85)
+ *   bisip_model_percentile   <- utils.get_model_percentile (utils.py:17-35)
  *
  * Layouts (all row-major, float64):
  *   theta   [n_spectra][n_theta][ndim]      parameter vectors (order as the reference's
@@ -41,7 +42,7 @@
 extern "C" {
 #endif
 
-#define BISIP_ABI_VERSION 1
+#define BISIP_ABI_VERSION 2
 
 enum bisip_model {
   BISIP_MODEL_COLECOLE = 0, /* PeltonColeCole, models.py:232 */
@@ -155,17 +156,37 @@ int bisip_ensemble_run(const bisip_model_desc *desc, int n_spectra, int n_walker
 /*
  * Column statistics of data[n_spectra][n_samples][n_cols] (a flat chain is
  * [n_keep*n_walkers][ndim]): exact order statistics with NumPy's default 'linear'
- * interpolation, mean and population std (ddof=0).
+ * interpolation, mean and population std (ddof=0).  The data is read in place (one CTA per
+ * column keeps it in shared memory when n_samples <= ~27,000, else strided global reads).
  *   pct_lo[n_pct] int64: floor of the virtual index q/100*(n_samples-1)
  *   pct_gamma[n_pct]   : its fractional part (both computed by the host exactly like NumPy)
  *   pct_out [n_spectra][n_pct][n_cols]; mean_out, std_out [n_spectra][n_cols] (may be NULL)
- *   workspace: device scratch of bisip_column_stats_workspace(...) bytes.
+ *   workspace, workspace_bytes: unused since ABI 2 (pass NULL, 0); bisip_column_stats_workspace returns 0.
  */
 int64_t bisip_column_stats_workspace(int n_spectra, int64_t n_samples, int n_cols);
 int bisip_column_stats(const double *data, int n_spectra, int64_t n_samples, int n_cols,
                        int n_pct, const int64_t *pct_lo, const double *pct_gamma,
                        double *pct_out, double *mean_out, double *std_out,
                        void *workspace, int64_t workspace_bytes, void *stream);
+
+/*
+ * Percentiles of the forward model over a chain, fused (replaces utils.get_model_percentile,
+ * utils.py:17-35: one forward() per flat-chain sample into an (n, 2, N) array, then
+ * np.percentile over axis 0).  One CTA per model column evaluates it for all n_theta parameter
+ * vectors into shared memory and selects there: the (n_theta, 2N) model matrix is never
+ * written to memory.
+ *   theta   [n_spectra][n_theta][ndim]
+ *   pct_out [n_spectra][n_pct][2][n_freq]
+ * The decomposition is evaluated in its collapsed FP64 column form for every desc->precision;
+ * ColeCole n_modes and Decomp n_coef (<= 32) are not limited to the sampler kernels' tile shapes.
+ * BISIP_ERR_UNSUPPORTED when n_theta exceeds one CTA's shared memory (~27,000): compose
+ * bisip_forward + bisip_column_stats instead.
+ */
+int bisip_model_percentile(const bisip_model_desc *desc, int n_spectra, int64_t n_theta,
+                           const double *theta, const double *w, int64_t w_stride,
+                           const double *taus, const double *log_taus, int64_t tau_stride,
+                           int n_pct, const int64_t *pct_lo, const double *pct_gamma,
+                           double *pct_out, void *stream);
 
 #ifdef __cplusplus
 }

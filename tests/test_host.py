@@ -148,7 +148,7 @@ def test_c_abi_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert _lib.load().bisip_abi_version() == 1
+    assert _lib.load().bisip_abi_version() == _lib.ABI_VERSION == 2
     out = subprocess.run(['nm', '-D', '--defined-only', _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert all(re.search(rf'\bT {n}\b', out) for n in declared)
 
