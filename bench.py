@@ -11,14 +11,18 @@ shard: on-device ensemble sampling, kept-chain write (discard 1000, thin 10), de
 mean / std summary, and for N>1 the NCCL all-gather of the summaries.
 
 `value`  : inputs (zn, zn_err, p0) already resident in HBM; timed with CUDA events, max over ranks.
-`e2e`    : the same job through the public API (BatchInversion.fit) from pinned HOST buffers, with the
-           host->device copies of the inputs and the device->host read of the summaries inside the
-           timed region.
+`e2e`    : the same job through the public API (BatchInversion.fit_gathered) from pinned HOST buffers, with the
+           host->device copies of the inputs, for N>1 the NCCL gather of the summaries, and the device->host read
+           of the complete result inside the timed region.
 `roofline`: ensemble_decomp kernel (the dominant launch): algorithmic flops (17,792 per eval,
            SURVEY.md §8d) / its CUDA-event duration, against the FP64 DMMA peak measured on this
            box by tools/peaks (MEASURED_PEAKS.json has no FP64 figure).
 `variants`: the collapsed FP64 kernel (precision='fp64-collapsed') and the TF32 / 3xTF32 tcgen05 kernels on the same
            shard (kernel alone on a slice, and the whole shard end to end), next to the default FP64 DMMA numbers.
+`configs` : BASELINE configs 2-4 on one GPU (N=1 only): Cole-Cole(2) on the bundled spectrum, Dias / Shin on 1,024 synthetic
+           spectra, and the 256-tau decomposition on 10,000 spectra in FP64 DMMA / 3xTF32 / TF32 / collapsed FP64 — kernel
+           alone, end to end, and a roofline fraction each.
+`strong_scaling`: the fixed 100,000-spectra survey through ONE `bisip_b200.fit_sharded` call on the N ranks.
 `cpu_baseline`: the reference's own Cython + NumPy log-probability (oracle/_ref) under the emcee
            restatement, on all host cores, on a bounded sample of the same spectra.
 `--impl reference`: that CPU arm alone, as its own JSON line.
@@ -36,24 +40,12 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# stdout carries exactly ONE line, the JSON result: native libraries (NCCL's version banner under NCCL_DEBUG, ncu,
-# the CUDA runtime) print to file descriptor 1 behind Python's back, so fd 1 is pointed at stderr for the whole run
-# and the JSON line goes to a private duplicate of the original stdout.
-_JSON_OUT = None
-
-
-def _claim_stdout():
-    global _JSON_OUT
-    if _JSON_OUT is None:
-        sys.stdout.flush()
-        _JSON_OUT = os.fdopen(os.dup(1), "w")
-        os.dup2(2, 1)
-
-
+# This script prints exactly ONE line to stdout, the JSON result (its own progress goes to stderr).  File descriptor 1
+# itself is left alone: whatever the driver's instrumentation makes native libraries print there (NCCL's banner under
+# NCCL_DEBUG, ...) stays visible to the driver, and no environment variable of the driver is rewritten.
 def emit(line):
-    out = _JSON_OUT or sys.stdout
-    out.write(json.dumps(line) + "\n")
-    out.flush()
+    sys.stdout.write(json.dumps(line) + "\n")
+    sys.stdout.flush()
 
 # ---- workload (BASELINE config 5 shard) ------------------------------------------------------
 N_FREQ, N_TAU, POLY_DEG, WALKERS, NSTEPS = 64, 64, 4, 256, 2000
@@ -208,18 +200,161 @@ def dmma_peak():
         return 37.2, 37.2, f"nominal (tools/peaks failed: {e})"
 
 
+def kernel_sources_sha():
+    """Hash of the sources that define the dominant kernel (ensemble_kernel<DecompEvaluator>): the committed ncu DRAM
+    figure is only quoted while they are unchanged."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("sampler.cuh", "decomp_eval.cuh", "common.cuh"):
+        with open(os.path.join(ROOT, "bisip_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def dfma_peak():
+    """FP64 vector (DFMA) peak of this GPU from tools/peaks (register-resident FMA loop)."""
+    exe = os.path.join(ROOT, "tools", "peaks")
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=180).stdout
+        return float(json.loads(out.strip().splitlines()[-1])["dfma_tflops"]), "measured live: tools/peaks (DFMA loop)"
+    except Exception as e:
+        return 36.8, f"round-1 measurement (tools/peaks failed: {e})"
+
+
+def ncu_flops_per_eval():
+    """Executed FP64 flops per log-prob evaluation of the vector-model kernels, counted once by ncu
+    (smsp__sass_thread_inst_executed_op_d{fma,mul,add}_pred_on) and committed in profiles/ncu_summary.json."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json"))).get("fp64_flop_per_eval", {})
+    except Exception:
+        return {}
+
+
+def measure_config(torch, engine, inv, p0_h, discard, thin, reps=2, warm=True):
+    """One BASELINE config on this GPU: the ensemble kernel alone (device-resident inputs, CUDA events) and the whole
+    job end to end through BatchInversion.fit (pinned host inputs in, host summaries out)."""
+    dev = inv.device
+    B, W, T = inv.n_spectra, inv.nwalkers, inv.nsteps
+    spec = inv._spec()
+    w_d = _dev(torch, inv.w, dev)
+    y_d, ye_d, p0_d = inv._zn.to(dev), inv._zn_err.to(dev), p0_h.to(dev)
+    bounds_d = _dev(torch, inv.param_bounds, dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best, res = 1e30, None
+    for rep in range(reps + (1 if warm else 0)):
+        c = p0_d.clone()
+        del res
+        e0.record()
+        res = engine.ensemble_run(spec, c, w_d, y_d, ye_d, bounds_d, nsteps=T, seed=inv.seed, spectrum0=0,
+                                  discard=discard, thin=thin, store_chain=True, store_logp=False)
+        e1.record()
+        torch.cuda.synchronize()
+        if rep or not warm:
+            best = min(best, e0.elapsed_time(e1))
+    acc = float(res['accepted'].double().mean().item() / T)
+    nan = int((res['flags'] != 0).sum().item())
+    del res, c
+    torch.cuda.empty_cache()
+    e2e = 1e30
+    for rep in range(reps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = inv.fit(p0=p0_h, discard=discard, thin=thin, percentiles=PCT)
+        torch.cuda.synchronize()
+        e2e = min(e2e, time.perf_counter() - t0)
+    evals = float(B) * W * T
+    out = {"spectra": B, "walkers": W, "nsteps": T, "kernel_ms": best, "evals_per_s": evals * (T + 1) / T / (best * 1e-3),
+           "e2e_ms": 1e3 * e2e, "e2e_evals_per_s": evals / e2e, "e2e_spectra_per_s": B / e2e,
+           "acceptance_fraction": acc, "nan_flags": nan,
+           "h2d_bytes": int(inv._zn.numel() * 16 + p0_h.numel() * 8), "d2h_bytes": int(sum(v.nbytes for v in r.values()))}
+    del r
+    torch.cuda.empty_cache()
+    return out
+
+
+def _dev(torch, a, dev):
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64))).to(dev)
+
+
+def run_other_configs(torch, engine, synthetic, BatchInversion, _lib, dev, peak_dmma, peak_dfma):
+    """BASELINE configs 2-4 on one GPU (config 1 is the reference's own CPU-sized case; config 5 is the headline)."""
+    out = {}
+    fl = ncu_flops_per_eval()
+    f, w = synthetic.frequencies(N_FREQ)
+
+    def fwd_for(model, **kw):
+        probe = BatchInversion(model, w, np.zeros((1, 2, N_FREQ)), np.ones((1, 2, N_FREQ)), device=dev, **kw)
+        return lambda th, ww: engine.forward(probe._spec(), _dev(torch, th[:, None, :], dev), _dev(torch, ww, dev))[:, 0].cpu().numpy()
+
+    def pin(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+
+    # ---- C3: Dias2000 and Shin2015, 1,024 synthetic 64-frequency spectra, 128 walkers x 2000 steps
+    for model in ("dias", "shin"):
+        syn = synthetic.make(model, 0, 1024, fwd_for(model), N=N_FREQ)
+        inv = BatchInversion(model, w, pin(syn['zn']), pin(syn['zn_err']), nwalkers=128, nsteps=2000, seed=SEED, device=dev)
+        r = measure_config(torch, engine, inv, pin(inv.draw_p0(0, 1024)), DISCARD, THIN)
+        fpe = fl.get(f"ensemble_{model}")
+        r["roofline"] = ({"bound": "fp64 pipe", "fp64_flop_per_eval": fpe, "achieved": r["evals_per_s"] * fpe / 1e12,
+                          "peak": peak_dfma, "unit": "TFLOP/s", "frac": r["evals_per_s"] * fpe / 1e12 / peak_dfma,
+                          "flop_source": fl.get("source")} if fpe else None)
+        out[f"C3_{model}"] = dict(workload=f"{model}: 1,024 synthetic {N_FREQ}-frequency spectra, 128 walkers x 2000 steps", **r)
+    # ---- C2: ColeCole n_modes=2 on the bundled example spectrum, 64 walkers x 2000 steps, batched x 1,024 streams
+    from bisip_b200.data import example_tables
+    from bisip_b200.utils import prepare_data
+    d = prepare_data(example_tables()['SIP-K389175'], 'mrad')
+    inv = BatchInversion('colecole', d['w'], pin(np.repeat(d['zn'][None], 1024, 0)), pin(np.repeat(d['zn_err'][None], 1024, 0)),
+                         nwalkers=64, nsteps=2000, n_modes=2, seed=SEED, device=dev)
+    r = measure_config(torch, engine, inv, pin(inv.draw_p0(0, 1024)), DISCARD, THIN)
+    fpe = fl.get("ensemble_colecole2_n20")
+    r["roofline"] = ({"bound": "fp64 pipe", "fp64_flop_per_eval": fpe, "achieved": r["evals_per_s"] * fpe / 1e12, "peak": peak_dfma,
+                      "unit": "TFLOP/s", "frac": r["evals_per_s"] * fpe / 1e12 / peak_dfma, "flop_source": fl.get("source")} if fpe else None)
+    out["C2_colecole2"] = dict(workload="ColeCole n_modes=2, bundled SIP-K389175 (20 frequencies), 64 walkers x 2000 steps, "
+                                        "1,024 independent streams of the same spectrum in one launch", **r)
+    # ---- C4: decomposition with 256 taus, 10,000 synthetic spectra, 256 walkers x 2000 steps: FP64 DMMA vs TF32 / 3xTF32 / collapsed
+    n4 = env_int("BISIP_BENCH_C4_SPECTRA", 10000)
+    syn = synthetic.make('decomp', 0, n4, fwd_for('decomp', poly_deg=POLY_DEG, n_tau=256), N=N_FREQ, poly_deg=POLY_DEG, n_tau=256)
+    zn_h, ze_h = pin(syn['zn']), pin(syn['zn_err'])
+    flop4 = 2 * (POLY_DEG + 1) * 256 + 2 * 256 * 2 * N_FREQ + 6 * 2 * N_FREQ          # 68,864
+    c4, p0_h, ref_pct = {}, None, None
+    th_chk = None
+    for prec in ("fp64", "3xtf32", "tf32", "fp64-collapsed"):
+        inv = BatchInversion('decomp', w, zn_h, ze_h, nwalkers=WALKERS, nsteps=NSTEPS, poly_deg=POLY_DEG, n_tau=256,
+                             precision=prec, seed=SEED, device=dev)
+        if p0_h is None:
+            p0_h = pin(inv.draw_p0(0, n4))
+        r = measure_config(torch, engine, inv, p0_h, DISCARD, THIN, reps=1, warm=(prec != "fp64"))
+        r["kernel"] = engine.decomp_kernel_kind(inv._spec(), N_FREQ, WALKERS)
+        if prec == "fp64":
+            r["roofline"] = {"bound": "tensor", "algorithmic_flop_per_eval": flop4, "achieved": r["evals_per_s"] * flop4 / 1e12,
+                             "peak": peak_dmma, "unit": "TFLOP/s", "frac": r["evals_per_s"] * flop4 / 1e12 / peak_dmma}
+            ref_pct = inv.results['percentiles'].copy()
+            ref_sd = inv.results['std'].copy()
+            th_chk = _dev(torch, inv.results['percentiles'][:64, 1][:, None, :], dev)          # posterior medians of 64 spectra
+            z_ref = engine.forward(inv._spec(), th_chk, _dev(torch, w, dev))
+        else:
+            z = engine.forward(inv._spec(), th_chk, _dev(torch, w, dev))
+            r["forward_rel_error_vs_fp64"] = float(((z - z_ref).abs().amax((2, 3)) / z_ref.abs().amax((2, 3))).max().item())
+            r["max_median_shift_in_posterior_sd"] = float(np.max(np.abs(inv.results['percentiles'][:, 1] - ref_pct[:, 1]) / ref_sd))
+            r["speedup_vs_fp64"] = r["evals_per_s"] / c4["fp64"]["evals_per_s"]
+        c4[prec] = r
+        del inv
+        torch.cuda.empty_cache()
+    out["C4_decomp_256taus"] = {"workload": f"Debye decomposition poly_deg={POLY_DEG}, 256 taus, {n4} synthetic {N_FREQ}-frequency spectra, "
+                                            f"{WALKERS} walkers x {NSTEPS} steps; kernel alone + end to end per precision", **c4}
+    return out
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
     from bisip_b200 import _lib, engine, synthetic
-    from bisip_b200.batch import BatchInversion, gather
+    from bisip_b200.batch import BatchInversion, fit_sharded, gather_packed
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":     # its banner goes to stdout, next to the JSON line
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     B = SPECTRA_PER_GPU
     b0 = rank * B                                      # weak scaling: rank r owns spectra [rB, (r+1)B)
@@ -247,8 +382,8 @@ def run_gpu(args):
     y_d, ye_d, p0_d = zn_h.to(dev), ze_h.to(dev), p0_h.to(dev)
     bounds_d = _lib.dev_f64(inv.param_bounds, dev)
     coords = torch.empty_like(p0_d)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    kern_ms = []
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+    kern_ms, stats_ms = [], []
 
     def step_resident(timed):
         coords.copy_(p0_d)
@@ -257,13 +392,15 @@ def run_gpu(args):
                                   discard=DISCARD, thin=THIN, store_chain=True, store_logp=False)
         ev[1].record()
         st = engine.column_stats(res['chain'].reshape(B, nk * WALKERS, inv.ndim), p=list(PCT), want_mean=True, want_std=True)
+        ev[2].record()
         out = {'percentiles': st['pct'], 'mean': st['mean'], 'std': st['std'],
                'acceptance_fraction': res['accepted'].to(torch.float64).mean(1) / NSTEPS}
         if world > 1:
-            out = gather(out, B * world, rank, world)
+            out = gather_packed(out, B * world, rank, world)
         if timed:
             torch.cuda.synchronize()
             kern_ms.append(ev[0].elapsed_time(ev[1]))
+            stats_ms.append(ev[1].elapsed_time(ev[2]))
         return out, res
 
     def barrier():
@@ -297,42 +434,72 @@ def run_gpu(args):
     value = evals_step / (ms_step * 1e-3)
     acc = float(out['acceptance_fraction'].mean().item())
     flags_bad = 0
+    del out
+    torch.cuda.empty_cache()
 
-    # ---- end-to-end arm: public API, pinned host inputs, host results ---------------------------------
+    # ---- end-to-end arm: public API, pinned host inputs in, COMPLETE host result out on every rank (for N > 1 the NCCL
+    #      gather of the summaries is inside the timed region: BatchInversion.fit_gathered = fit + gather_packed) ---------
     h2d = zn_h.numel() * 8 + ze_h.numel() * 8 + p0_h.numel() * 8 + syn['w'].nbytes
     e2e_ms = []
     d2h = 0
-    for i in range(max(1, args.steps)):
+    for i in range(max(1, min(args.steps, env_int("BISIP_BENCH_E2E_STEPS", 5)))):
         barrier()
         t0 = time.perf_counter()
-        r = inv.fit(p0=p0_h, discard=DISCARD, thin=THIN, percentiles=PCT)
+        r = inv.fit_gathered(B * world, p0=p0_h, discard=DISCARD, thin=THIN, percentiles=PCT)
         torch.cuda.synchronize()
         e2e_ms.append(1e3 * (time.perf_counter() - t0))
         d2h = sum(v.nbytes for v in r.values())
         flags_bad += int((r['flags'] != 0).sum())
+        assert r['mean'].shape[0] == B * world
     te = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = evals_step / (float(te.item()) * 1e-3)
+    r_local = {k: v[b0:b0 + B] for k, v in r.items()}
 
-    # ---- reduced-precision variants of the same workload (north_star: "a TF32/3xTF32 variant compared against it"):
-    #      the tcgen05 kernel on a 592-spectra slice of this rank's shard, ensemble kernel alone, CUDA events.
-    #      Reported next to the FP64 numbers; `value`, `e2e` and `roofline` stay FP64.
     # ---- the collapsed FP64 path end to end on EVERY rank (weak scaling of the fast path: at N=8 this is the whole
-    #      100,000-spectra survey), max over ranks like `e2e`
+    #      100,000-spectra survey, summaries gathered), max over ranks like `e2e`
     alt = BatchInversion('decomp', syn['w'], zn_h, ze_h, nwalkers=WALKERS, nsteps=NSTEPS, poly_deg=POLY_DEG,
                          n_tau=N_TAU, seed=SEED, spectrum_offset=b0, device=dev, precision='fp64-collapsed')
     col_best = 1e30
-    for rep in range(2):
+    for rep in range(3):
         barrier()
         t0 = time.perf_counter()
-        r_col = alt.fit(p0=p0_h, discard=DISCARD, thin=THIN, percentiles=PCT)
+        r_col = alt.fit_gathered(B * world, p0=p0_h, discard=DISCARD, thin=THIN, percentiles=PCT)
         torch.cuda.synchronize()
         tc = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tc, op=dist.ReduceOp.MAX)
         col_best = min(col_best, float(tc.item()))
+    r_col = {k: v[b0:b0 + B] for k, v in r_col.items()}
     del alt
+
+    # ---- strong scaling: the FIXED 100,000-spectra survey through ONE sharded product call (fit_sharded: full-size host
+    #      arrays in on every rank, complete result out on every rank), default FP64 DMMA path.  The survey is this rank's
+    #      12,500 synthetic spectra tiled to 100,000 (each copy samples its own Philox stream); fit_sharded reads only the
+    #      rank's block of it.
+    strong = None
+    n_strong = env_int("BISIP_BENCH_STRONG_SPECTRA", 100000)
+    if n_strong > 0:
+        reps = -(-n_strong // B)                        # the survey = this rank's shard data tiled (Philox streams differ per index)
+        zn_s = zn_h.repeat(reps, 1, 1)[:n_strong]
+        ze_s = ze_h.repeat(reps, 1, 1)[:n_strong]
+        prec_s = os.environ.get("BISIP_BENCH_STRONG_PRECISION", "fp64")
+        barrier()
+        t0 = time.perf_counter()
+        rs = fit_sharded('decomp', syn['w'], zn_s, ze_s, discard=DISCARD, thin=THIN, percentiles=PCT, nwalkers=WALKERS,
+                         nsteps=NSTEPS, poly_deg=POLY_DEG, n_tau=N_TAU, seed=SEED, device=dev, precision=prec_s)
+        torch.cuda.synchronize()
+        ts = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        strong = {"spectra": n_strong, "n_gpus": world, "precision": prec_s, "seconds": float(ts.item()),
+                  "evals_per_s": n_strong * WALKERS * NSTEPS / float(ts.item()), "spectra_per_s": n_strong / float(ts.item()),
+                  "api": "bisip_b200.fit_sharded (full host arrays in, shard_range per rank, p0 drawn per spectrum, NCCL gather "
+                         "of the summaries, complete host result on every rank); scaling = strong",
+                  "complete_on_this_rank": bool(rs['mean'].shape[0] == n_strong), "nan_flags": int((rs['flags'] != 0).sum())}
+        del rs, zn_s, ze_s
+        torch.cuda.empty_cache()
 
     variants = {}
     if rank == 0:
@@ -344,13 +511,13 @@ def run_gpu(args):
             best = 1e30
             for rep in range(3):
                 c = p0_d[:nv].clone()
-                ev[2].record()
+                ev[3].record()
                 r_alt = engine.ensemble_run(aspec, c, w_d, y_d[:nv], ye_d[:nv], bounds_d, nsteps=500, seed=SEED, spectrum0=b0,
                                             discard=250, thin=10, store_chain=True, store_logp=False)
-                ev[3].record()
+                ev[4].record()
                 torch.cuda.synchronize()
                 if rep:
-                    best = min(best, ev[2].elapsed_time(ev[3]))
+                    best = min(best, ev[3].elapsed_time(ev[4]))
             variants[prec] = {"kernel": engine.decomp_kernel_kind(aspec, N_FREQ, WALKERS), "evals_per_s": nv * WALKERS * 501 / (best * 1e-3),
                               "spectra": nv, "steps": 500, "kernel_ms": best,
                               "acceptance_fraction": float(r_alt['accepted'].double().mean().item() / 500),
@@ -370,18 +537,20 @@ def run_gpu(args):
                                    "e2e_ms_per_step": 1e3 * best, "e2e_nan_flags": int((r_alt['flags'] != 0).sum()),
                                    "e2e_gpus": 1})
         del r_alt, alt
-        # FP64 to rounding: the collapsed sampler takes the same decisions as the two-stage DMMA path (`r` = last e2e
+        # FP64 to rounding: the collapsed sampler takes the same decisions as the two-stage DMMA path (`r_local` = last e2e
         # result of this rank) unless a ~1e-13 log-prob rounding difference flips one of the shard's 1.3e10 accept tests
         # (expected: a fraction of one spectrum per shard); from there on that spectrum's chain is a different, equally
         # valid draw
-        same = np.all(r_col['percentiles'] == r['percentiles'], axis=(1, 2))
-        shift = np.abs(r_col['percentiles'][:, 1] - r['percentiles'][:, 1]) / r['std']
+        same = np.all(r_col['percentiles'] == r_local['percentiles'], axis=(1, 2))
+        shift = np.abs(r_col['percentiles'][:, 1] - r_local['percentiles'][:, 1]) / r_local['std']
         variants['fp64-collapsed'].update({
             "e2e_evals_per_s": B * world * WALKERS * NSTEPS / col_best, "e2e_spectra_per_s": B * world / col_best,
             "e2e_ms_per_step": 1e3 * col_best, "e2e_nan_flags": int((r_col['flags'] != 0).sum()), "e2e_gpus": world,
             "e2e_spectra": B * world, "spectra_with_percentiles_identical_to_fp64": int(same.sum()),
             "spectra_compared": B, "max_median_shift_in_posterior_sd": float(shift.max()),
             "algorithmic_flop_per_eval": 2 * 2 * N_FREQ * (POLY_DEG + 1 + 2)})
+    del y_d, ye_d, p0_d, coords
+    torch.cuda.empty_cache()
     if rank == 0:
         k_ms = float(np.mean(kern_ms))
         flops_launch = FLOP_PER_EVAL * float(B) * WALKERS * (NSTEPS + 1)       # +1: log-prob of p0
@@ -391,17 +560,26 @@ def run_gpu(args):
         if os.path.exists(summ) and B == 12500:          # the committed ncu figure is for the default shard size
             try:
                 e = json.load(open(summ)).get("ensemble_decomp", {})
-                traffic, traffic_src = e.get("dram_bytes_per_launch_at_bench_size"), e.get("dram_bytes_source")
+                if e.get("kernel_sources_sha") == kernel_sources_sha():
+                    traffic, traffic_src = e.get("dram_bytes_per_launch_at_bench_size"), e.get("dram_bytes_source")
+                else:
+                    traffic_src = ("not quoted: the kernel sources changed since the committed ncu capture "
+                                   f"({e.get('kernel_sources_sha')} -> {kernel_sources_sha()}); re-run tools/ncu_summary.py")
             except Exception:
                 traffic = None
-        # CPU baseline (bounded sample of the same spectra, all host cores)
+        # CPU baseline (bounded sample of the same spectra, all host cores) and BASELINE configs 2-4: N=1 only
         cores = host_cores()
+        other = None
         if world == 1:
             cpu_v, cpu_wall, cpu_sample = reference_sample(syn['zn'], syn['zn_err'], syn['w'], min(cores, B))
             cpu_baseline = {"value": cpu_v, "unit": "evals/s", "cores": min(cores, B), "kind": "reference", "sample": cpu_sample,
                             "wall_s": cpu_wall, "evals_per_s_per_core": cpu_v / min(cores, B),
                             "extrapolated_days_for_full_config_on_these_cores": 1e5 * WALKERS * NSTEPS / cpu_v / 86400.0,
                             "note": "reference models.py + Cython (oracle/_ref) under oracle/emcee_restatement.py"}
+            if env_int("BISIP_BENCH_CONFIGS", 1):
+                peak_dfma, _ = dfma_peak()
+                other = run_other_configs(torch, engine, synthetic, BatchInversion, _lib, dev, peak_sust, peak_dfma)
+                other["fp64_vector_peak_tflops"] = peak_dfma
         else:       # the host-core baseline is a property of the box, not of N: timed at N=1 only (the other ranks would wait)
             cpu_baseline = {"value": None, "unit": "evals/s", "cores": cores, "kind": "reference",
                             "sample": "not run at N>1: see the N=1 line"}
@@ -412,11 +590,12 @@ def run_gpu(args):
             "config": {"workload": WORKLOAD, "spectra_per_gpu": B, "walkers": WALKERS, "nsteps": NSTEPS, "n_freq": N_FREQ,
                        "n_tau": N_TAU, "poly_deg": POLY_DEG, "discard": DISCARD, "thin": THIN, "percentiles": list(PCT),
                        "l2": "per-step inputs (p0 154 MB) and outputs (kept chain 15 GB) exceed the 126 MB L2; no flush needed",
-                       "parallelism": f"{world} x independent shards, NCCL all-gather of summaries only"},
+                       "parallelism": f"{world} x independent shards, one NCCL all-gather of the packed summaries"},
             "spectra_per_s": B * world / (ms_step * 1e-3),
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": float(te.item()), "spectra_per_s": B * world / (float(te.item()) * 1e-3),
-                    "api": "bisip_b200.BatchInversion.fit (pinned host zn/zn_err/p0 in, host summaries out)"},
+                    "api": "bisip_b200.BatchInversion.fit_gathered (pinned host zn/zn_err/p0 of the shard in; for N>1 the NCCL "
+                           "gather of the summaries is inside the timed region; the complete host result on every rank)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "ensemble_kernel<DecompEvaluator<4>> (bisip_ensemble_run)",
                          "achieved": achieved, "peak": peak_sust, "unit": "TFLOP/s", "frac": achieved / peak_sust,
@@ -425,9 +604,13 @@ def run_gpu(args):
                                                           + WALKERS * 12 + 4 * N_FREQ * 8 + 4),
                          "peak_source": peak_src, "peak_burst": peak_burst,
                          "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_step,
+                         "stats_kernel_ms": float(np.mean(stats_ms)),
+                         "stats_kernel_GBps": float(B) * nk * WALKERS * inv.ndim * 8 / (float(np.mean(stats_ms)) * 1e-3) / 1e9,
                          "algorithmic_flop_per_eval": FLOP_PER_EVAL},
             "cpu_baseline": cpu_baseline,
             "clocks": clk, "acceptance_fraction": acc, "nan_flags": flags_bad,
+            "strong_scaling": strong,
+            "configs": other,
             "variants": {"note": "other decomposition kernels on the same shard: evals_per_s = ensemble kernel alone on a slice (CUDA "
                                  "events), e2e_* = the whole shard through BatchInversion.fit like `e2e`.  fp64-collapsed is FP64 "
                                  "(same 1e-12 parity, z = (L K) a); tf32 / 3xtf32 tolerances in profiles/r01f_tf32_study.md.  "
@@ -452,7 +635,6 @@ def main():
         os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                                    f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                                    "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:])
-    _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -10,8 +10,9 @@ summaries on the device (``bisip_column_stats``); chains never visit the host un
 Multi-GPU: spectra are independent, so rank ``r`` of ``G`` owns the contiguous block
 ``shard_range(B, r, G)`` and no collective runs during sampling.  The Philox counter carries
 the *global* spectrum index, so results do not depend on ``G`` or on the sub-batch size.
-``gather`` all-gathers the per-spectrum summaries (NCCL on GPU tensors; gloo on CPU tensors
-in the unit tests).
+``fit_sharded`` is the product-level entry point: full arrays in, complete result out on every rank
+(``gather_packed``: one NCCL all-gather of the packed summaries; ``gather_chain_to_rank0``: optional chunked gather of
+the kept chains).  ``gather`` is the per-tensor variant (NCCL on GPU tensors; gloo on CPU tensors in the unit tests).
 """
 import numpy as np
 import torch
@@ -77,6 +78,94 @@ def gather(local, n_total, rank, world, group=None):
     return out
 
 
+def gather_packed(local, n_total, rank, world, group=None):
+    """``gather`` with ONE collective: every per-spectrum tensor is flattened to float64 columns of one
+    (per, width) buffer, all-gathered once, and split again (int tensors are exact in float64 up to 2^53)."""
+    import torch.distributed as dist
+    per = -(-n_total // world)
+    keys = sorted(local)
+    first = local[keys[0]]
+    n_loc = first.shape[0]
+    cols = [local[k].reshape(n_loc, -1).to(torch.float64) for k in keys]
+    widths = [c.shape[1] for c in cols]
+    pad = torch.zeros((per, sum(widths)), dtype=torch.float64, device=first.device)
+    pad[:n_loc] = torch.cat(cols, 1)
+    full = torch.empty((world * per, sum(widths)), dtype=torch.float64, device=first.device)
+    dist.all_gather_into_tensor(full, pad, group=group)
+    out, c0 = {}, 0
+    for k, wd in zip(keys, widths):
+        t = full[:n_total, c0:c0 + wd].reshape((n_total,) + tuple(local[k].shape[1:]))
+        out[k] = t.to(local[k].dtype)
+        c0 += wd
+    return out
+
+
+def gather_chain_to_rank0(chain, n_total, rank, world, group=None, chunk_bytes=1 << 28):
+    """Chunked gather of per-spectrum chains (n_local, ...) to rank 0: at most ``chunk_bytes`` per rank in flight,
+    so a survey's (thinned) chains never need a second device-resident copy.  Returns the (n_total, ...) host array
+    on rank 0 and None elsewhere.  Every rank makes the same number of collective calls."""
+    import torch.distributed as dist
+    per = -(-n_total // world)
+    item = int(np.prod(chain.shape[1:])) * chain.element_size()
+    step = max(1, int(chunk_bytes // max(1, item)))
+    out = np.empty((n_total,) + tuple(chain.shape[1:]), dtype=np.float64) if rank == 0 else None
+    for c0 in range(0, per, step):
+        c1 = min(per, c0 + step)
+        buf = torch.zeros((c1 - c0,) + tuple(chain.shape[1:]), dtype=chain.dtype, device=chain.device)
+        k = max(0, min(chain.shape[0], c1) - c0)
+        if k > 0:
+            buf[:k] = chain[c0:c0 + k]
+        parts = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+        dist.gather(buf, parts, dst=0, group=group)
+        if rank == 0:
+            for r in range(world):
+                g0 = r * per + c0
+                kk = max(0, min(n_total, r * per + c1) - g0)
+                if kk > 0:
+                    out[g0:g0 + kk] = parts[r][:kk].cpu().numpy()
+    return out
+
+
+def fit_sharded(model, w, zn, zn_err, discard=0, thin=1, percentiles=(2.5, 50, 97.5), p0=None, gather_chain=False,
+                group=None, batch_size=None, **kwargs):
+    """Invert a whole survey on all ranks of the current ``torch.distributed`` job (one process per GPU).
+
+    The reference inverts a batch as a serial loop over files (``docs/tutorials/decomposition.ipynb`` cells 9-10);
+    here every rank takes the FULL arrays (``w`` (N,) or (B, N); ``zn``, ``zn_err`` (B, 2, N); optional ``p0``
+    (B, W, ndim)), inverts its contiguous block ``shard_range(B, rank, world)`` with ``BatchInversion`` (Philox
+    counters carry the global spectrum index: the result does not depend on the number of ranks), and the
+    per-spectrum summaries are all-gathered with one NCCL collective, so every rank returns the complete result:
+    ``percentiles`` (B, len(p), ndim), ``mean``, ``std`` (B, ndim), ``acceptance_fraction``, ``flags`` (B,).
+    With ``gather_chain=True`` the kept chains (``discard`` / ``thin``) are gathered to rank 0 in chunks
+    (``chain`` (B, n_keep, W, ndim) on rank 0, None elsewhere).  Without an initialised process group it runs the
+    whole survey on the current device.  ``kwargs`` go to ``BatchInversion`` (nwalkers, nsteps, poly_deg, ...)."""
+    import torch.distributed as dist
+    on = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank(group) if on else 0
+    world = dist.get_world_size(group) if on else 1
+    B = int(zn.shape[0])
+    lo, hi = shard_range(B, rank, world)
+    w_arr = np.asarray(w, dtype=np.float64)
+    inv = BatchInversion(model, w_arr if w_arr.ndim == 1 else w_arr[lo:hi], zn[lo:hi], zn_err[lo:hi],
+                         spectrum_offset=lo + int(kwargs.pop('spectrum_offset', 0)), **kwargs)
+    dev_res = inv.fit_device(None if p0 is None else p0[lo:hi], discard, thin, percentiles, gather_chain, batch_size)
+    chain = dev_res.pop('chain', None)
+    dev_res.pop('log_prob', None)
+    if on and world > 1:
+        full = gather_packed(dev_res, B, rank, world, group)
+        chain_all = gather_chain_to_rank0(chain, B, rank, world, group) if gather_chain else None
+    else:
+        full = dev_res
+        chain_all = chain.cpu().numpy() if gather_chain else None
+    out = {k: v.cpu().numpy() for k, v in full.items()}
+    if gather_chain:
+        out['chain'] = chain_all
+    out['shard'] = (lo, hi)
+    inv.results, inv.percentiles = out, tuple(float(q) for q in percentiles)
+    out['inversion'] = inv
+    return out
+
+
 class BatchInversion:
     """Invert ``B`` spectra that share a model (and its bounds) on one GPU.
 
@@ -90,15 +179,21 @@ class BatchInversion:
         poly_deg, c_exp, n_tau, precision: PolynomialDecomposition options.
         n_modes: Cole-Cole modes.
         seed: Philox key.  spectrum_offset: global index of the first spectrum (for shards).
+        nan_policy: what ``fit`` does when a spectrum's log-probability was NaN (``results['flags'] != 0``; emcee
+            raises ``ValueError`` for a single spectrum): 'warn' (default), 'raise' or 'ignore'.
     """
 
     def __init__(self, model, w, zn, zn_err, nwalkers=32, nsteps=5000, bounds=None, poly_deg=5, c_exp=1.0,
-                 n_tau=None, precision='fp64', n_modes=1, seed=0, spectrum_offset=0, a=2.0, device=None):
+                 n_tau=None, precision='fp64', n_modes=1, seed=0, spectrum_offset=0, a=2.0, device=None,
+                 nan_policy='warn'):
         if model not in _MODEL_IDS:
             raise ValueError(f'unknown model {model!r}')
         self.model = model
         self.nwalkers, self.nsteps = int(nwalkers), int(nsteps)
         self.seed, self.spectrum_offset, self.a = int(seed), int(spectrum_offset), float(a)
+        if nan_policy not in ('warn', 'raise', 'ignore'):
+            raise ValueError("nan_policy must be 'warn', 'raise' or 'ignore'")
+        self.nan_policy = nan_policy
         self.device = _lib.require_cuda(device)
         self.param_names, dflt = default_bounds(model, poly_deg, n_modes)
         self.param_bounds = dflt if bounds is None else np.asarray(bounds, dtype=np.float64)
@@ -146,6 +241,20 @@ class BatchInversion:
             out[i - lo] = rng.uniform(lob, hib, (self.nwalkers, self.ndim))
         return out
 
+    def _validate(self, p0):
+        """The checks ``Inversion.fit`` inherits from emcee, for the whole batch at once."""
+        if self.param_bounds.shape != (2, self.ndim) or len(self.param_names) != self.ndim:
+            raise ValueError(f'bounds must be (2, {len(self.param_names)}) for model {self.model!r}, got {self.param_bounds.shape}')
+        if self.nwalkers < 2 * self.ndim:
+            raise RuntimeError("It is unadvisable to use a red-blue move with fewer walkers than "
+                               "twice the number of dimensions.")
+        if p0 is not None:
+            if tuple(p0.shape) != (self.n_spectra, self.nwalkers, self.ndim):
+                raise ValueError("incompatible input dimensions {0}".format(tuple(p0.shape)))
+            fin = torch.isfinite(p0).all() if isinstance(p0, torch.Tensor) else np.isfinite(p0).all()
+            if not bool(fin):
+                raise ValueError("At least one parameter value was infinite or NaN")
+
     def max_batch(self, n_keep, keep_chain):
         free, _ = torch.cuda.mem_get_info(self.device)
         # kept chain (+ log-prob when the chain is kept); the statistics read it in place: no workspace
@@ -161,18 +270,41 @@ class BatchInversion:
         ``acceptance_fraction`` (B,), ``flags`` (B,), and with ``keep_chain`` the kept
         ``chain`` (B, n_keep, W, ndim) and ``log_prob`` (B, n_keep, W).
         """
-        dev_res = self.fit_device(p0, discard, thin, percentiles, keep_chain, batch_size)
+        dev_res = self.fit_device(p0, discard, thin, percentiles, keep_chain, batch_size, _chain_to_host=True)
+        self.percentiles = tuple(float(q) for q in percentiles)
+        self.results = {k: (v if isinstance(v, np.ndarray) else v.cpu().numpy()) for k, v in dev_res.items()}
+        bad = int(np.count_nonzero(self.results['flags']))
+        if bad and self.nan_policy != 'ignore':
+            msg = (f"Probability function returned NaN for {bad} of {self.n_spectra} spectra "
+                   "(results['flags'] != 0; emcee raises ValueError for a single spectrum)")
+            if self.nan_policy == 'raise':
+                raise ValueError(msg)
+            import warnings
+            warnings.warn(msg, RuntimeWarning)
+        return self.results
+
+    def fit_gathered(self, n_total, p0=None, discard=0, thin=1, percentiles=(2.5, 50, 97.5), group=None, batch_size=None):
+        """``fit`` for a shard-local inversion inside a ``torch.distributed`` job: this object holds spectra
+        ``[spectrum_offset, spectrum_offset + n_spectra)`` of a survey of ``n_total`` sharded by ``shard_range``; after
+        sampling, the summaries of all ranks are all-gathered (one NCCL collective) and the COMPLETE result
+        (``n_total`` rows, host arrays) is returned on every rank.  Without a process group it equals ``fit``."""
+        import torch.distributed as dist
+        dev_res = self.fit_device(p0, discard, thin, percentiles, False, batch_size)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dev_res = gather_packed(dev_res, int(n_total), dist.get_rank(group), dist.get_world_size(group), group)
         self.percentiles = tuple(float(q) for q in percentiles)
         self.results = {k: v.cpu().numpy() for k, v in dev_res.items()}
         return self.results
 
     def fit_device(self, p0=None, discard=0, thin=1, percentiles=(2.5, 50, 97.5), keep_chain=False,
-                   batch_size=None):
-        """Same as ``fit`` but leaves the summaries on the GPU (for the NCCL gather)."""
+                   batch_size=None, _chain_to_host=False):
+        """Same as ``fit`` but leaves the summaries on the GPU (for the NCCL gather).  With ``keep_chain`` the kept
+        chains of all sub-batches stay on the device too (``fit`` moves each sub-batch's chain to the host instead)."""
         B, W, ndim = self.n_spectra, self.nwalkers, self.ndim
         nk = engine.n_keep(self.nsteps, discard, thin)
         if nk == 0:
             raise ValueError('discard/thin leave no samples')
+        self._validate(p0)
         bs = int(batch_size) if batch_size else self.max_batch(nk, keep_chain)
         bounds = _lib.dev_f64(self.param_bounds, self.device)
         shared_w = self.w.ndim == 1
@@ -196,10 +328,13 @@ class BatchInversion:
             acc['std'].append(st['std'])
             acc['acceptance_fraction'].append(res['accepted'].to(torch.float64).mean(1) / float(self.nsteps))
             acc['flags'].append(res['flags'])
-            if keep_chain:
+            if keep_chain and _chain_to_host:      # sub-batching stays effective: nothing accumulates on the device
+                acc['chain'].append(res['chain'].cpu().numpy())
+                acc['log_prob'].append(res['log_prob'].cpu().numpy())
+            elif keep_chain:
                 acc['chain'].append(res['chain'])
                 acc['log_prob'].append(res['log_prob'])
-        return {k: torch.cat(v, 0) for k, v in acc.items()}
+        return {k: (np.concatenate(v, 0) if isinstance(v[0], np.ndarray) else torch.cat(v, 0)) for k, v in acc.items()}
 
     # ------------------------------------------------------------------ results
     def rtd(self, stat='mean'):
@@ -243,10 +378,15 @@ class BatchInversion:
     # ------------------------------------------------------------------ construction from files
     @classmethod
     def from_files(cls, model, filepaths, headers=1, ph_units='mrad', **kwargs):
-        """Vectorised ingest of many data files that share a frequency grid or not
-        (reference ``utils.py:108-146`` applied per file)."""
+        """Vectorised ingest of many data files (reference ``utils.py:108-146`` applied per file).  The files must
+        hold the SAME NUMBER of frequencies (one kernel launch has one n_freq); their frequency values may differ
+        (then ``w`` is per spectrum).  Group files of different length and build one ``BatchInversion`` per group."""
         from .utils import prepare_data
         data = [prepare_data(np.loadtxt(fp, skiprows=headers, delimiter=','), ph_units) for fp in filepaths]
+        lengths = sorted({d['N'] for d in data})
+        if len(lengths) != 1:
+            raise ValueError(f'from_files needs files with the same number of frequencies, got N in {lengths}; '
+                             'group the files by length')
         ws = np.stack([d['w'] for d in data])
         w = ws[0] if np.all(ws == ws[0]) else ws
         inv = cls(model, w, np.stack([d['zn'] for d in data]), np.stack([d['zn_err'] for d in data]), **kwargs)

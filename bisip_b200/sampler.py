@@ -71,6 +71,14 @@ class EnsembleSampler:
 
     # ------------------------------------------------------------------ run
     def run_mcmc(self, initial_state, nsteps, progress=False, **kwargs):
+        """emcee's ``run_mcmc(initial_state, nsteps, progress=...)``; returns the last ``(coords, log_prob)`` pair
+        (emcee returns a ``State``, which unpacks to the same two leading items).  ``progress`` is accepted and
+        ignored (the whole chain is one kernel launch).  emcee's other ``sample`` keywords change what is stored
+        (``thin_by``, ``store``, ``tune``, ``skip_initial_state_check`` ...) and have no counterpart here: passing
+        one raises instead of silently returning a chain with different semantics."""
+        if kwargs:
+            raise NotImplementedError('run_mcmc keyword(s) not supported by the on-device sampler: '
+                                      + ', '.join(sorted(kwargs)) + ' (use get_chain(discard=, thin=) instead)')
         if initial_state is None:
             if self._last is None:
                 raise ValueError("Cannot have `initial_state=None` if run_mcmc has never been called.")

@@ -284,3 +284,116 @@ def test_bench_reference_arm_prints_one_json_line():
     quiet = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1'],
                            capture_output=True, text=True, env=dict(env, RANK='1', WORLD_SIZE='2'), timeout=600)
     assert quiet.returncode == 0 and quiet.stdout == ''
+
+
+_SHARDED_WORKER = r'''
+import os, sys
+sys.path.insert(0, os.environ["BISIP_ROOT"])
+import numpy as np, torch, torch.distributed as dist
+import bisip_b200
+from bisip_b200 import _lib, batch
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + os.environ["PORT"],
+                        rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = dist.get_rank(), dist.get_world_size()
+# the device work is stubbed: per-spectrum results are functions of the GLOBAL spectrum index, on CPU tensors
+_lib.require_cuda = lambda device=None: torch.device("cpu")
+def fake_fit_device(self, p0=None, discard=0, thin=1, percentiles=(2.5, 50, 97.5), keep_chain=False, batch_size=None,
+                    _chain_to_host=False):
+    g = torch.arange(self.spectrum_offset, self.spectrum_offset + self.n_spectra, dtype=torch.float64)
+    assert p0 is None or p0.shape[0] == self.n_spectra
+    out = {"percentiles": g[:, None, None] + torch.arange(len(percentiles) * self.ndim, dtype=torch.float64).reshape(1, len(percentiles), self.ndim),
+           "mean": g[:, None] * torch.ones(1, self.ndim, dtype=torch.float64), "std": 0.5 * g[:, None] * torch.ones(1, self.ndim, dtype=torch.float64),
+           "acceptance_fraction": 0.01 * g, "flags": (g % 3 == 0).to(torch.int32)}
+    if keep_chain:
+        out["chain"] = g[:, None, None, None] * torch.ones(1, 4, self.nwalkers, self.ndim, dtype=torch.float64)
+        out["log_prob"] = torch.zeros(self.n_spectra, 4, self.nwalkers, dtype=torch.float64)
+    return out
+batch.BatchInversion.fit_device = fake_fit_device
+B, N = 11, 8
+w = np.logspace(3, -1, N)
+zn = np.zeros((B, 2, N)); ze = np.ones((B, 2, N))
+p0 = np.zeros((B, 12, 5))
+res = bisip_b200.fit_sharded("dias", w, zn, ze, discard=2, thin=1, p0=p0, gather_chain=True, nwalkers=12, nsteps=10)
+assert res["shard"] == batch.shard_range(B, rank, world)
+assert res["mean"].shape == (B, 5) and res["percentiles"].shape == (B, 3, 5) and res["flags"].dtype == np.int32
+np.testing.assert_array_equal(res["mean"][:, 0], np.arange(B))
+np.testing.assert_array_equal(res["percentiles"][:, 2, 4], np.arange(B) + 14)
+np.testing.assert_array_equal(res["flags"], (np.arange(B) % 3 == 0).astype(np.int32))
+np.testing.assert_allclose(res["acceptance_fraction"], 0.01 * np.arange(B))
+if rank == 0:
+    assert res["chain"].shape == (B, 4, 12, 5)
+    np.testing.assert_array_equal(res["chain"][:, 1, 3, 2], np.arange(B))
+else:
+    assert res["chain"] is None
+# tiny chunks: several collective rounds, ragged last shard
+ch = torch.arange(*batch.shard_range(B, rank, world), dtype=torch.float64)[:, None] * torch.ones(1, 7, dtype=torch.float64)
+full = batch.gather_chain_to_rank0(ch, B, rank, world, chunk_bytes=2 * 7 * 8)
+if rank == 0:
+    np.testing.assert_array_equal(full[:, 3], np.arange(B))
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_fit_sharded_two_ranks_gloo(tmp_path):
+    """Product-level multi-GPU entry point (full arrays in, complete result on every rank, chains to rank 0) on a
+    world-size-2 gloo group; the per-rank device work is stubbed so the test runs on CPU."""
+    script = tmp_path / "worker_sharded.py"
+    script.write_text(_SHARDED_WORKER)
+    port = str(29900 + os.getpid() % 90)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", PORT=port, BISIP_ROOT=ROOT)
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=180)
+        assert p.returncode == 0, out
+        assert "ok" in out
+
+
+def test_cython_funcs_surface_and_argument_checks():
+    """bisip_b200.cython_funcs exports the reference's four native names (cython_funcs.pyx:49-108) and applies Cython's
+    typed-buffer checks BEFORE touching the GPU (so they are testable here)."""
+    import inspect
+    from bisip_b200 import cython_funcs as cf
+    sig = {n: list(inspect.signature(getattr(cf, n)).parameters) for n in cf.__all__}
+    assert sig == {'ColeCole_cyth': ['w', 'R0', 'm', 'lt', 'c'],
+                   'Dias2000_cyth': ['w', 'R0', 'm', 'log_tau', 'eta', 'delta'],
+                   'Decomp_cyth': ['w', 'taus', 'log_taus', 'c_exp', 'R0', 'a'],
+                   'Shin2015_cyth': ['w', 'R', 'log_Q', 'n']}
+    w = np.array([1.0, 2.0])
+    with pytest.raises(ValueError, match='Buffer dtype mismatch'):
+        cf.Dias2000_cyth(w.astype(np.float32), 1.0, 0.25, -10.0, 5.0, 0.5)
+    with pytest.raises(ValueError, match='wrong number of dimensions'):
+        cf.Decomp_cyth(w, np.ones(3), np.ones(3), 1.0, 1.0, np.ones(1))
+    with pytest.raises(TypeError):
+        cf.ColeCole_cyth([1.0, 2.0], 1.0, np.array([0.3]), np.array([-2.0]), np.array([0.5]))
+    with pytest.raises(TypeError):
+        cf.Shin2015_cyth(w, np.array([0.5, 0.5]), np.array([-14.0, -6.0]), 'n')
+
+
+def test_batch_validation_and_run_mcmc_kwargs(monkeypatch):
+    """emcee's up-front checks apply to batches too; unsupported run_mcmc keywords raise (no silent semantics change)."""
+    import torch
+    from bisip_b200 import _lib
+    from bisip_b200.batch import BatchInversion
+    from bisip_b200.sampler import EnsembleSampler
+    monkeypatch.setattr(_lib, 'require_cuda', lambda device=None: torch.device('cpu'))
+    w = np.logspace(3, -1, 8)
+    zn, ze = np.zeros((3, 2, 8)), np.ones((3, 2, 8))
+    with pytest.raises(RuntimeError):
+        BatchInversion('dias', w, zn, ze, nwalkers=8, nsteps=10).fit_device()
+    with pytest.raises(ValueError, match='bounds must be'):
+        BatchInversion('dias', w, zn, ze, nwalkers=16, nsteps=10, bounds=np.zeros((2, 4))).fit_device()
+    with pytest.raises(ValueError, match='incompatible input dimensions'):
+        BatchInversion('dias', w, zn, ze, nwalkers=16, nsteps=10).fit_device(p0=np.zeros((3, 15, 5)))
+    p0 = np.zeros((3, 16, 5)); p0[1, 2, 3] = np.nan
+    with pytest.raises(ValueError, match='infinite or NaN'):
+        BatchInversion('dias', w, zn, ze, nwalkers=16, nsteps=10).fit_device(p0=p0)
+    with pytest.raises(ValueError):
+        BatchInversion('dias', w, zn, ze, nan_policy='maybe')
+    from bisip_b200 import engine
+    s = EnsembleSampler(16, 5, engine.ModelSpec(model=_lib.MODEL_DIAS, ndim=5), w, zn[0], ze[0], np.zeros((2, 5)), seed=1)
+    with pytest.raises(NotImplementedError, match='thin_by'):
+        s.run_mcmc(np.zeros((16, 5)), 10, thin_by=2)
