@@ -65,7 +65,8 @@ int check_desc(const bisip_model_desc* d) {
     case BISIP_MODEL_DECOMP:
       if (d->n_tau <= 0 || d->n_coef <= 0) return fail(BISIP_ERR_BAD_ARG, "Decomp n_tau/n_coef must be positive");
       if (d->ndim != 1 + d->n_coef) return fail(BISIP_ERR_BAD_ARG, "Decomp ndim != 1+n_coef");
-      if (d->n_coef > 8) return fail(BISIP_ERR_UNSUPPORTED, "Decomp poly_deg > 7 not supported");
+      if (d->n_coef > 8 && !(d->precision == BISIP_PREC_FP64_COLLAPSED && d->n_coef <= 30))
+        return fail(BISIP_ERR_UNSUPPORTED, "Decomp poly_deg > 7 needs precision 'fp64-collapsed' (poly_deg <= 29)");
       if (d->precision < BISIP_PREC_FP64 || d->precision > BISIP_PREC_FP64_COLLAPSED)
         return fail(BISIP_ERR_BAD_ARG, "unknown precision");
       break;
@@ -190,6 +191,19 @@ int bisip_ensemble_run(const bisip_model_desc* desc, int n_spectra, int n_walker
   const int rp = sampler_rows_pad(n_walkers);
   size_t smem = sampler_smem_bytes(n_walkers, desc->ndim);
   dim3 grid(n_spectra);
+  // Warp-private sampler (sampler_wp.cuh) for the evaluators that have a warp-level form, up to 256 walkers.
+  // BISIP_SAMPLER=classic forces the block-synchronous kernel (developer comparison; both follow the same stream).
+  {
+    const char* e = getenv("BISIP_SAMPLER");
+    const bool classic = e && !strcmp(e, "classic");
+    if (!classic && n_walkers <= 256) {
+      if (desc->model == BISIP_MODEL_DECOMP && desc->precision == BISIP_PREC_FP64_COLLAPSED && desc->n_coef <= 30)
+        return launch_ens_wp_collapsed(P, grid, st);
+      if (desc->model == BISIP_MODEL_DIAS || desc->model == BISIP_MODEL_SHIN ||
+          (desc->model == BISIP_MODEL_COLECOLE && desc->n_modes <= 2))
+        return launch_ens_wp_vec(P, grid, st);
+    }
+  }
   switch (desc->model) {
     case BISIP_MODEL_COLECOLE:
       smem += vec_smem_doubles(desc->n_freq, rp, vec_row_consts(*desc)) * 8;

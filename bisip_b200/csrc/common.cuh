@@ -39,6 +39,27 @@ __device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
                    1.0 / 9007199254740992.0);
 }
 
+// The same number built on the INTEGER pipe: (a>>5) 2^26 + (b>>6) is a 53-bit integer m, and m 2^-53 is exact in
+// binary64, so assembling sign / exponent / mantissa from clz gives the identical bits without the two int->double
+// conversions, the multiply and the add — FP64-pipe instructions that, in the sampler's serial phases, queue behind
+// the co-resident warps' DMMA / DFMA streams (ncu: the FP64 ops of those phases draw 5-8x the stall samples of an
+// integer op).
+__device__ __forceinline__ double u53_int(uint32_t a, uint32_t b) {
+  const unsigned long long m = ((unsigned long long)(a >> 5) << 26) | (unsigned long long)(b >> 6);
+  const int lz = __clzll((long long)m);                       // m < 2^53: lz >= 11
+  const unsigned long long mant = (m << (lz + 1)) >> 12;      // drop the leading one; the 12 bits shifted out are zero
+  const unsigned long long bits = ((unsigned long long)(1033 - lz) << 52) | mant;
+  return m ? __longlong_as_double((long long)bits) : 0.0;
+}
+
+// float -> double widening (exact) on the integer pipe; denormal floats flush to zero (callers pass O(1) numbers)
+__device__ __forceinline__ double f32_widen_int(float f) {
+  const uint32_t b = __float_as_uint(f);
+  const uint32_t e = (b >> 23) & 0xffu;
+  const uint32_t hi = (b & 0x80000000u) | ((e + 896u) << 20) | ((b >> 3) & 0xfffffu);
+  return e ? __hiloint2double((int)hi, (int)(b << 29)) : 0.0;
+}
+
 // ---------------------------------------------------------------- FP64 tensor tiles
 // mma.sync .f64 lowers to DMMA.8x8x4 on sm_100a (tools/peaks.cu verifies the fragment maps):
 //   A (16xK):  a[i] -> row g + 8*(i&1), col t + 4*(i>>1)

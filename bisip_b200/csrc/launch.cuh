@@ -173,6 +173,8 @@ int launch_ens_umma(const EnsembleParams& P, dim3 grid, const UmmaPlan& plan, cu
 int launch_ens_collapsed(const EnsembleParams& P, dim3 grid, size_t smem, cudaStream_t st);                  // ens_collapsed.cu
 int launch_ens_colecole(const EnsembleParams& P, dim3 grid, size_t smem, cudaStream_t st);                   // ens_colecole.cu
 int launch_ens_dias_shin(const EnsembleParams& P, dim3 grid, size_t smem, cudaStream_t st);                  // ens_dias_shin.cu
+int launch_ens_wp_collapsed(const EnsembleParams& P, dim3 grid, cudaStream_t st);                            // ens_wp_collapsed.cu
+int launch_ens_wp_vec(const EnsembleParams& P, dim3 grid, cudaStream_t st);                                  // ens_wp_vec.cu
 int run_batch_decomp(const BatchParams& P, bool want_z, cudaStream_t st);                                    // batch_decomp.cu
 int run_batch_vec(const BatchParams& P, bool want_z, cudaStream_t st);                                       // batch_vec.cu
 

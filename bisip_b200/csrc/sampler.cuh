@@ -8,8 +8,9 @@
 //   purpose 0      shuffle keys: walker i <- word (i&3) of index (i>>2), low bits replaced by i so
 //                  that keys are unique: key = (word & ~mask) | i, mask = 2^ceil(log2 W) - 1;
 //                  walkers ranked by key; ranks [0,H0) = split 0, [H0,W) = split 1, H0 = (W+1)/2
-//   purpose 1+2s   proposal p of split s: u = u53(x,y) -> zz = ((a-1)u+1)^2/a ; partner = mulhi(z, Nc)
-//   purpose 2+2s   proposal p of split s: acceptance draw u53(x,y)
+//   purpose 1+s    proposal p of split s, ONE call for all its draws: u = u53(x,y) -> zz = ((a-1)u+1)^2/a ;
+//                  partner = mulhi(z, Nc) ; acceptance draw u2 = u53(w, (z << 16) | 0x8000): 43 random bits (w and
+//                  the low half of z, which the partner index does not depend on), centred so that u2 > 0
 #pragma once
 #include "common.cuh"
 #include "decomp_eval.cuh"
@@ -64,11 +65,11 @@ struct SamplerSmem {
   double* prop;    // [rows_pad][ndim]
   double* chi;     // [rows_pad]
   double* zz;      // [2][rows_pad]  stretch factors, double-buffered by half-step parity
-  double* u2;      // [rows_pad]     acceptance uniforms (FP64 fallback of the accept test)
+  double* u2;      // [2][rows_pad]  acceptance uniforms (FP64 fallback of the accept test), by half-step parity
   double* bnd;     // [2][ndim]
   double* red;     // [kWarps]
   long long* bkey; // [2][ndim] ordered-integer image of bnd
-  double* lf;      // [rows_pad]     (ndim-1) ln zz - ln u, evaluated in FP32 (accept filter), stored widened
+  double* lf;      // [2][rows_pad]  (ndim-1) ln zz - ln u, evaluated in FP32 (accept filter), stored widened
   uint32_t* keys;  // [Wpad4]        shuffle keys of the NEXT step
   int* list;       // [2][W]         walker at rank, double-buffered by step parity
   int* acc;        // [W]
@@ -82,7 +83,7 @@ __host__ __device__ inline int sampler_rows_pad(int W) { return ceil_div((W + 1)
 
 __host__ __device__ inline size_t sampler_smem_bytes(int W, int ndim) {
   const int rp = sampler_rows_pad(W);
-  size_t dbl = (size_t)W * ndim + W + (size_t)rp * ndim + rp + 2 * rp + rp + rp + 4 * ndim + kWarps;
+  size_t dbl = (size_t)W * ndim + W + (size_t)rp * ndim + rp + 2 * rp + 2 * rp + 2 * rp + 4 * ndim + kWarps;
   size_t words = (size_t)(W + 4) + 2 * W + W + rp + rp + 260 + (W + 4);
   return dbl * 8 + words * 4 + 48;
 }
@@ -94,8 +95,8 @@ __device__ inline void sampler_carve(SamplerSmem& s, double* base, int W, int nd
   s.prop = base; base += (size_t)rp * ndim;
   s.chi = base; base += rp;
   s.zz = base; base += 2 * rp;
-  s.u2 = base; base += rp;
-  s.lf = base; base += rp;
+  s.u2 = base; base += 2 * rp;
+  s.lf = base; base += 2 * rp;
   s.bnd = base; base += 2 * ndim;
   s.red = base; base += kWarps;
   s.bkey = reinterpret_cast<long long*>(base); base += 2 * ndim;
@@ -615,16 +616,25 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
       }
     }
   };
-  // proposal draws of half-step (t, sp): stretch factor zz and partner index
+  // all draws of half-step (t, sp) from one Philox call per proposal: stretch factor zz, partner index, acceptance
+  // uniform u2 and the FP32 image of the accept threshold
   auto gen_proposal_draws = [&](uint32_t t, int sp, int worker, int nworkers) {
     const int Hs = sp ? W - H0 : H0, Nc = W - Hs;
     double* zzb = s.zz + (size_t)sp * rows_pad;
+    double* u2b = s.u2 + (size_t)sp * rows_pad;
+    double* lfb = s.lf + (size_t)sp * rows_pad;
     for (int q = worker; q < Hs; q += nworkers) {
-      const u32x4 r = philox4x32_10((uint32_t)q, t, spec, (uint32_t)(1 + 2 * sp), k0, k1);
+      const u32x4 r = philox4x32_10((uint32_t)q, t, spec, (uint32_t)(1 + sp), k0, k1);
       const double u = u53(r.x, r.y);
       const double zr = __dadd_rn(__dmul_rn(P.a - 1.0, u), 1.0);
-      zzb[q] = P.a_pow2 ? __dmul_rn(__dmul_rn(zr, zr), P.inv_a) : __ddiv_rn(__dmul_rn(zr, zr), P.a);
+      const double zz = P.a_pow2 ? __dmul_rn(__dmul_rn(zr, zr), P.inv_a) : __ddiv_rn(__dmul_rn(zr, zr), P.a);
+      const double u2 = u53(r.w, (r.z << 16) | 0x8000u);
+      zzb[q] = zz;
       s.partner[q] = (int)__umulhi(r.z, (uint32_t)Nc);
+      u2b[q] = u2;
+      // MUFU.LG2-based logarithms: |error| <= ~4e-6 here (zz in [1/a, a]; |ln u| <= 31 at 2^-22 relative), far
+      // inside the 2^-12 margin below which accept_filter() hands the decision to the FP64 logarithms
+      lfb[q] = (double)((float)(ndim - 1) * __logf((float)zz) - __logf((float)u2));
     }
   };
 
@@ -650,25 +660,16 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
       const int off = sp ? H0 : 0, Hs = sp ? W - H0 : H0;
       const int coff = sp ? 0 : H0;
       const double* zzb = s.zz + (size_t)sp * rows_pad;
-      // ---- PROPOSE: threads [0,Hs) build q = c_j - (c_j - s_k) zz ; the other threads draw the
-      //      acceptance uniforms of this half-step and the FP32 image of the accept threshold ----------
+      const double* u2b = s.u2 + (size_t)sp * rows_pad;
+      const double* lfb = s.lf + (size_t)sp * rows_pad;
+      // ---- PROPOSE: threads [0,Hs) build q = c_j - (c_j - s_k) zz (all random draws of this half-step were
+      //      produced during the previous accept phase) -----------------------------------------------------
       FINE_START
-      for (int idx = tid; idx < 2 * Hs; idx += NT) {
-        if (idx < Hs) {
-          const int q = idx;
-          const int j = list[coff + s.partner[q]];
-          const int k = list[off + q];
-          s.inb[q] = propose_and_check(s.coords + j * ndim, s.coords + k * ndim, zzb[q], s.prop + q * ndim, s.bkey, ndim) ? 1 : 0;
-          ev.prepare_row(q, s.prop + q * ndim);
-        } else {
-          const int q = idx - Hs;
-          const u32x4 r = philox4x32_10((uint32_t)q, t, spec, (uint32_t)(2 + 2 * sp), k0, k1);
-          const double u2 = u53(r.x, r.y);
-          s.u2[q] = u2;
-          // MUFU.LG2-based logarithms: |error| <= ~4e-6 here (zz in [1/a, a]; |ln u| <= 37 at 2^-22 relative), far
-          // inside the 2^-12 margin below which accept_filter() hands the decision to the FP64 logarithms
-          s.lf[q] = (double)((float)(ndim - 1) * __logf((float)zzb[q]) - __logf((float)u2));
-        }
+      for (int q = tid; q < Hs; q += NT) {
+        const int j = list[coff + s.partner[q]];
+        const int k = list[off + q];
+        s.inb[q] = propose_and_check(s.coords + j * ndim, s.coords + k * ndim, zzb[q], s.prop + q * ndim, s.bkey, ndim) ? 1 : 0;
+        ev.prepare_row(q, s.prop + q * ndim);
       }
       FINE_MARK(6)
       __syncthreads();
@@ -692,11 +693,11 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
           // emcee: accept iff (ndim-1) ln zz + lp' - lp > ln u.  The logarithms were taken in FP32
           // (|error| < 1e-5): unless the margin is below the threshold the FP64 decision is already
           // determined; otherwise (about 1 proposal in 10^4) it is recomputed in FP64 as the oracle does.
-          const double est = __dsub_rn(lpn, lpo) + s.lf[q];
+          const double est = __dsub_rn(lpn, lpo) + lfb[q];
           bool accept;
           if (!accept_filter(est, lpn, lpo, accept)) {
             const double lnpdiff = __dsub_rn(__dadd_rn(__dmul_rn((double)(ndim - 1), log(zzb[q])), lpn), lpo);
-            accept = lnpdiff > log(s.u2[q]);
+            accept = lnpdiff > log(u2b[q]);
           }
           if (accept) {
             copy_dims(s.coords + k * ndim, s.prop + q * ndim, ndim);

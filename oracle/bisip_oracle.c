@@ -210,8 +210,10 @@ static inline double u53(uint32_t a, uint32_t b) { /* NumPy legacy random_sample
  *   purpose 0: shuffle keys — walker i uses word (i&3) of counter index (i>>2) with its low
  *              ceil(log2 W) bits replaced by i (unique keys); walkers are ranked by key;
  *              ranks [0,H0) form split 0, [H0,W) split 1, H0=(W+1)/2
- *   purpose 1+2s: proposal p of split s: u=u53(x0,x1); partner = mulhi(x2, Nc)
- *   purpose 2+2s: proposal p of split s: accept draw u53(x0,x1)
+ *   purpose 1+s: proposal p of split s, ONE call for all its draws: stretch u = u53(x0,x1);
+ *              partner = mulhi(x2, Nc); accept draw u2 = u53(x3, (x2 << 16) | 0x8000) — 43 random
+ *              bits (x3 and the low half of x2, which the partner index does not depend on),
+ *              centred so that u2 > 0
  * chain (nkeep,W,ndim), logp (nkeep,W): steps t with t>=discard+thin-1 and
  * (t-(discard+thin-1))%thin==0 (emcee backend.get_value slicing).  accepted (W) int32.
  * coords (W,ndim) in: p0, out: final ensemble.  Returns 0, or 1 if a NaN log-prob was seen.
@@ -227,6 +229,7 @@ int oracle_ensemble_run(const oracle_problem *p, double *coords, int W, int nste
   double *q = (double *)malloc(sizeof(double) * (size_t)H0 * ndim);
   double *lpq = (double *)malloc(sizeof(double) * (size_t)H0);
   double *fac = (double *)malloc(sizeof(double) * (size_t)H0);
+  double *lu2 = (double *)malloc(sizeof(double) * (size_t)H0);
   uint32_t *keys = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)W);
   int *list = (int *)malloc(sizeof(int) * (size_t)W);
   int nan_seen = 0;
@@ -256,9 +259,10 @@ int oracle_ensemble_run(const oracle_problem *p, double *coords, int W, int nste
       const int off = s ? H0 : 0, Hs = s ? W - H0 : H0;
       const int coff = s ? 0 : H0, Nc = W - Hs;
       for (int pp = 0; pp < Hs; ++pp) {
-        uint32_t ctr[4] = {(uint32_t)pp, t, spectrum, (uint32_t)(1 + 2 * s)}, x[4];
+        uint32_t ctr[4] = {(uint32_t)pp, t, spectrum, (uint32_t)(1 + s)}, x[4];
         oracle_philox4x32_10(ctr, key, x);
         double u = u53(x[0], x[1]);
+        lu2[pp] = log(u53(x[3], (x[2] << 16) | 0x8000u));
         double zr = (a - 1.0) * u + 1.0;
         double zz = zr * zr / a;
         int r = (int)(((uint64_t)x[2] * (uint64_t)Nc) >> 32);
@@ -272,9 +276,7 @@ int oracle_ensemble_run(const oracle_problem *p, double *coords, int W, int nste
         if (isnan(lpq[pp])) nan_seen = 1;
       }
       for (int pp = 0; pp < Hs; ++pp) {
-        uint32_t ctr[4] = {(uint32_t)pp, t, spectrum, (uint32_t)(2 + 2 * s)}, x[4];
-        oracle_philox4x32_10(ctr, key, x);
-        double lu = log(u53(x[0], x[1]));
+        double lu = lu2[pp];
         int k = list[off + pp];
         double lnpdiff = fac[pp] + lpq[pp] - lp[k];
         if (lnpdiff > lu) {
@@ -291,6 +293,6 @@ int oracle_ensemble_run(const oracle_problem *p, double *coords, int W, int nste
     }
   }
   if (lp_final) memcpy(lp_final, lp, sizeof(double) * (size_t)W);
-  free(Z); free(lp); free(q); free(lpq); free(fac); free(keys); free(list);
+  free(Z); free(lp); free(q); free(lpq); free(fac); free(lu2); free(keys); free(list);
   return nan_seen;
 }

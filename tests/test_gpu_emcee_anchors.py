@@ -15,7 +15,7 @@ import anchors as A
 
 pytestmark = pytest.mark.gpu
 ANCHORS = A.load()
-NSEEDS = 64
+NSEEDS = 256        # centre and scatter of the seed distribution to ~6 %: the z-scores are then properties of the notebook run
 
 
 def _batch_chains(anchor, pr, seeds):
@@ -32,19 +32,31 @@ def _batch_chains(anchor, pr, seeds):
     return res
 
 
+_BATCH_RUNS = {}
+
+
+def _batch_runs(name):
+    """Statistics of NSEEDS independent GPU runs of an anchor's configuration (cached for the session)."""
+    if name not in _BATCH_RUNS:
+        anchor = ANCHORS[name]
+        pr = A.problem(anchor)
+        res = _batch_chains(anchor, pr, list(range(NSEEDS)))
+        chains = res['chain']
+        assert chains.shape == (NSEEDS, anchor['nsteps'], anchor['nwalkers'], len(anchor['param_names']))
+        runs = [A.run_stats(anchor, c, pr['log_taus']) for c in chains]
+        _BATCH_RUNS[name] = (runs, A.autocorr_time(chains[:8], anchor), float(res['acceptance_fraction'].mean()))
+    return _BATCH_RUNS[name]
+
+
 @pytest.mark.parametrize("name", sorted(ANCHORS))
 def test_gpu_sampler_matches_real_emcee_notebook_output(name):
     anchor = ANCHORS[name]
-    pr = A.problem(anchor)
-    res = _batch_chains(anchor, pr, list(range(NSEEDS)))
-    chains = res['chain']
-    assert chains.shape == (NSEEDS, anchor['nsteps'], anchor['nwalkers'], len(anchor['param_names']))
-    runs = [A.run_stats(anchor, c, pr['log_taus']) for c in chains]
-    z = A.zscores(anchor, runs, tau=A.autocorr_time(chains[:8], anchor))
+    runs, tau, acc = _batch_runs(name)
+    z = A.zscores(anchor, runs, tau=tau)
     for key, v in z.items():
         assert np.all(np.abs(v) <= 3.0), (name, key, np.round(v, 2))
     # acceptance of the stretch move at these dimensions (emcee: 0.2 - 0.6 is healthy)
-    assert 0.25 < res['acceptance_fraction'].mean() < 0.7
+    assert 0.25 < acc < 0.7
 
 
 @pytest.mark.parametrize("name,nseeds", [('quickstart_cc1', 10), ('dias_K389172', 10), ('pelton_cc2_K389174', 8),
@@ -52,7 +64,8 @@ def test_gpu_sampler_matches_real_emcee_notebook_output(name):
 def test_class_api_matches_real_emcee_notebook_output(name, nseeds, data_files):
     """The notebook's own lines, through the drop-in classes: Model(filepath, ...); params.update(...); fit();
     get_param_mean / std / percentile(discard=, thin=) — p0 and the Philox key drawn from NumPy's global generator
-    like the reference does."""
+    like the reference does.  A handful of such runs must be draws of the distribution that the 256-seed batch (the
+    one z-tested against the notebook above) samples: same data ingest, bounds edits, discard / thin and statistics."""
     import bisip_b200 as bb
     anchor = ANCHORS[name]
     pr = A.problem(anchor)
@@ -77,9 +90,16 @@ def test_class_api_matches_real_emcee_notebook_output(name, nseeds, data_files):
             st['total_m'] = np.array([m.get_total_chargeability(**kw)])
         runs.append(st)
         chains.append(m.get_chain())
-    z = A.zscores(anchor, runs, tau=A.autocorr_time(chains[:4], anchor))
-    for key, v in z.items():
-        assert np.all(np.abs(v) <= 3.0), (name, key, np.round(v, 2))
+    batch, tau, _ = _batch_runs(name)
+    for key in runs[0]:
+        a = np.array([r[key] for r in runs])
+        b = np.array([r[key] for r in batch])
+        centre = np.median(b, axis=0)
+        scatter = np.maximum(1.4826 * np.median(np.abs(b - centre), axis=0),
+                             A.ess_standard_errors(anchor, np.median([r['std'] for r in batch], axis=0), tau).get(key, 0.0))
+        se = scatter * np.sqrt((np.pi / 2) * (1.0 / len(a) + 1.0 / len(b)))
+        zz = (np.median(a, axis=0) - centre) / se
+        assert np.all(np.abs(zz) <= 3.5), (name, key, np.round(zz, 2))
 
 
 def test_package_test_run_executes(capsys):

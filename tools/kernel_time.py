@@ -1,42 +1,64 @@
 #!/usr/bin/env python
-"""Time bisip_ensemble_run alone for a given shape (developer tool, not the bench).
-   python tools/kernel_time.py --model decomp --B 296 --W 256 --T 500 --N 64 --S 64 [--reps 3]"""
-import argparse, os, sys, json
-import numpy as np, torch
+"""Time one ensemble kernel configuration (developer tool; also the command profiled under ncu).
+
+    python tools/kernel_time.py --model decomp --precision fp64-collapsed --spectra 2368 --walkers 256 --steps 500
+    BISIP_B200_LIB=bisip_b200/csrc/libbisip_b200_dbg.so python tools/kernel_time.py ...   # per-phase cycle counters
+
+Synthetic spectra of the benchmark shape (bisip_b200/synthetic.py), kernel alone with CUDA events, best of --reps.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from bisip_b200 import _lib, engine, synthetic
-from bisip_b200.batch import BatchInversion
+import torch  # noqa: E402
+from bisip_b200 import _lib, engine, synthetic  # noqa: E402
+from bisip_b200.batch import BatchInversion  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--model", default="decomp"); ap.add_argument("--B", type=int, default=296)
-ap.add_argument("--W", type=int, default=256); ap.add_argument("--T", type=int, default=500)
-ap.add_argument("--N", type=int, default=64); ap.add_argument("--S", type=int, default=64)
-ap.add_argument("--P", type=int, default=4); ap.add_argument("--reps", type=int, default=3)
-ap.add_argument("--K", type=int, default=1)
-ap.add_argument("--precision", default="fp64"); ap.add_argument("--c_exp", type=float, default=1.0)
+ap.add_argument("--model", default="decomp")
+ap.add_argument("--precision", default="fp64")
+ap.add_argument("--spectra", type=int, default=2368)
+ap.add_argument("--walkers", type=int, default=256)
+ap.add_argument("--steps", type=int, default=500)
+ap.add_argument("--n-freq", type=int, default=64)
+ap.add_argument("--n-tau", type=int, default=64)
+ap.add_argument("--poly-deg", type=int, default=4)
+ap.add_argument("--n-modes", type=int, default=1)
+ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--keep", type=int, default=10, help="thin of the kept chain (discard = steps/2)")
 a = ap.parse_args()
-dev = torch.device("cuda:0")
-_, w = synthetic.frequencies(a.N)
-kw = dict(poly_deg=a.P, n_tau=a.S, c_exp=a.c_exp, precision=a.precision) if a.model == "decomp" else (dict(n_modes=a.K) if a.model == "colecole" else {})
-probe = BatchInversion(a.model, w, np.zeros((1, 2, a.N)), np.ones((1, 2, a.N)), device=dev, **kw)
+
+dev = _lib.require_cuda()
+f, w = synthetic.frequencies(a.n_freq)
+kw = dict(poly_deg=a.poly_deg, n_tau=a.n_tau, n_modes=a.n_modes)
+probe = BatchInversion(a.model, w, np.zeros((1, 2, a.n_freq)), np.ones((1, 2, a.n_freq)), device=dev, **kw)
 fwd = lambda th, ww: engine.forward(probe._spec(), _lib.dev_f64(th[:, None, :], dev), _lib.dev_f64(ww, dev))[:, 0].cpu().numpy()
-syn = synthetic.make(a.model, 0, a.B, fwd, N=a.N, poly_deg=a.P, n_modes=a.K, n_tau=a.S)
-inv = BatchInversion(a.model, w, syn["zn"], syn["zn_err"], nwalkers=a.W, nsteps=a.T, seed=1, device=dev, **kw)
-p0 = _lib.dev_f64(inv.draw_p0(0, a.B), dev)
-y, ye = _lib.dev_f64(syn["zn"], dev), _lib.dev_f64(syn["zn_err"], dev)
-wd, bd = _lib.dev_f64(w, dev), _lib.dev_f64(inv.param_bounds, dev)
+nsyn = min(a.spectra, 592)
+syn = synthetic.make(a.model, 0, nsyn, fwd, N=a.n_freq, poly_deg=a.poly_deg, n_modes=a.n_modes, n_tau=a.n_tau)
+reps = -(-a.spectra // nsyn)
+zn = np.tile(syn['zn'], (reps, 1, 1))[:a.spectra]
+ze = np.tile(syn['zn_err'], (reps, 1, 1))[:a.spectra]
+inv = BatchInversion(a.model, w, zn, ze, nwalkers=a.walkers, nsteps=a.steps, precision=a.precision, seed=7, device=dev, **kw)
 spec = inv._spec()
+p0 = _lib.dev_f64(inv.draw_p0(0, a.spectra), dev)
+w_d, y_d, ye_d, b_d = _lib.dev_f64(w, dev), _lib.dev_f64(zn, dev), _lib.dev_f64(ze, dev), _lib.dev_f64(inv.param_bounds, dev)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 best = 1e30
-for r in range(a.reps + 1):
+for rep in range(a.reps):
     c = p0.clone()
     e0.record()
-    res = engine.ensemble_run(spec, c, wd, y, ye, bd, nsteps=a.T, seed=1, discard=a.T // 2, thin=10, store_logp=False)
-    e1.record(); torch.cuda.synchronize()
-    if r: best = min(best, e0.elapsed_time(e1))
-evals = a.B * a.W * (a.T + 1)
-flop = 2 * (a.P + 1) * a.S + 2 * a.S * 2 * a.N + 12 * a.N
-print(json.dumps({"model": a.model, "B": a.B, "W": a.W, "T": a.T, "N": a.N, "S": a.S, "ms": best,
-                  "us_per_step": 1e3 * best / a.T, "evals_per_s": evals / best * 1e3,
-                  "tflops_alg": evals * flop / best / 1e9 if a.model == "decomp" else None,
-                  "acc": float(res["accepted"].double().mean() / a.T), "flags": int(res["flags"].sum())}))
+    res = engine.ensemble_run(spec, c, w_d, y_d, ye_d, b_d, nsteps=a.steps, seed=7, discard=a.steps // 2, thin=a.keep,
+                              store_chain=True, store_logp=False)
+    e1.record()
+    torch.cuda.synchronize()
+    best = min(best, e0.elapsed_time(e1))
+kind = engine.decomp_kernel_kind(spec, a.n_freq, a.walkers) if a.model == 'decomp' else a.model
+print(json.dumps({"model": a.model, "precision": a.precision, "kernel": kind, "spectra": a.spectra, "walkers": a.walkers,
+                  "steps": a.steps, "n_freq": a.n_freq, "n_tau": a.n_tau, "n_modes": a.n_modes, "ms": best,
+                  "evals_per_s": a.spectra * a.walkers * (a.steps + 1) / (best * 1e-3),
+                  "acceptance": float(res['accepted'].double().mean().item() / a.steps),
+                  "nan_flags": int((res['flags'] != 0).sum().item())}))
