@@ -199,8 +199,12 @@ int bisip_ensemble_run(const bisip_model_desc* desc, int n_spectra, int n_walker
     if (!classic && n_walkers <= 256) {
       if (desc->model == BISIP_MODEL_DECOMP && desc->precision == BISIP_PREC_FP64_COLLAPSED && desc->n_coef <= 30)
         return launch_ens_wp_collapsed(P, grid, st);
-      if (desc->model == BISIP_MODEL_DIAS || desc->model == BISIP_MODEL_SHIN ||
-          (desc->model == BISIP_MODEL_COLECOLE && desc->n_modes <= 2))
+      // measured (profiles/r02_wp_sweep.md): warp-private wins by 1.2-2x for <= 64 walkers or short spectra and for
+      // Cole-Cole everywhere; for Dias / Shin with > 64 walkers and > 32 frequencies the block-synchronous kernel is
+      // 2-6 % faster (its serial phases run on full warps; the long frequency loop dominates either way)
+      const bool long_vec = n_walkers > 64 && desc->n_freq > 32;
+      if ((desc->model == BISIP_MODEL_DIAS || desc->model == BISIP_MODEL_SHIN) ? !long_vec
+                                                                               : (desc->model == BISIP_MODEL_COLECOLE && desc->n_modes <= 2))
         return launch_ens_wp_vec(P, grid, st);
     }
   }

@@ -65,11 +65,11 @@ struct SamplerSmem {
   double* prop;    // [rows_pad][ndim]
   double* chi;     // [rows_pad]
   double* zz;      // [2][rows_pad]  stretch factors, double-buffered by half-step parity
-  double* u2;      // [2][rows_pad]  acceptance uniforms (FP64 fallback of the accept test), by half-step parity
   double* bnd;     // [2][ndim]
   double* red;     // [kWarps]
   long long* bkey; // [2][ndim] ordered-integer image of bnd
-  double* lf;      // [2][rows_pad]  (ndim-1) ln zz - ln u, evaluated in FP32 (accept filter), stored widened
+  float* lf;       // [2][rows_pad]  (ndim-1) ln zz - ln u2 in FP32 (accept filter), by half-step parity; the acceptance
+                   //                uniform itself is re-drawn from the Philox counter in the rare FP64 fallback
   uint32_t* keys;  // [Wpad4]        shuffle keys of the NEXT step
   int* list;       // [2][W]         walker at rank, double-buffered by step parity
   int* acc;        // [W]
@@ -83,7 +83,7 @@ __host__ __device__ inline int sampler_rows_pad(int W) { return ceil_div((W + 1)
 
 __host__ __device__ inline size_t sampler_smem_bytes(int W, int ndim) {
   const int rp = sampler_rows_pad(W);
-  size_t dbl = (size_t)W * ndim + W + (size_t)rp * ndim + rp + 2 * rp + 2 * rp + 2 * rp + 4 * ndim + kWarps;
+  size_t dbl = (size_t)W * ndim + W + (size_t)rp * ndim + rp + 2 * rp + rp + 4 * ndim + kWarps;
   size_t words = (size_t)(W + 4) + 2 * W + W + rp + rp + 260 + (W + 4);
   return dbl * 8 + words * 4 + 48;
 }
@@ -95,8 +95,7 @@ __device__ inline void sampler_carve(SamplerSmem& s, double* base, int W, int nd
   s.prop = base; base += (size_t)rp * ndim;
   s.chi = base; base += rp;
   s.zz = base; base += 2 * rp;
-  s.u2 = base; base += 2 * rp;
-  s.lf = base; base += 2 * rp;
+  s.lf = reinterpret_cast<float*>(base); base += rp;
   s.bnd = base; base += 2 * ndim;
   s.red = base; base += kWarps;
   s.bkey = reinterpret_cast<long long*>(base); base += 2 * ndim;
@@ -602,6 +601,8 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
   const int Wpad4 = (W + 3) & ~3;
   int kept = 0;
 
+  const bool a_is2 = P.a == 2.0;
+  const float am1f = (float)(P.a - 1.0), inv_af = (float)P.inv_a, nd1f = (float)(ndim - 1);
   // ---- work that depends only on the Philox stream runs one phase AHEAD of its use, on threads that
   //      would otherwise idle, so that the serial phases between two evaluations stay short ----------
   // shuffle keys of step t (emcee: shuffle(arange(W) % 2)): one Philox call feeds 4 walkers
@@ -621,20 +622,32 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
   auto gen_proposal_draws = [&](uint32_t t, int sp, int worker, int nworkers) {
     const int Hs = sp ? W - H0 : H0, Nc = W - Hs;
     double* zzb = s.zz + (size_t)sp * rows_pad;
-    double* u2b = s.u2 + (size_t)sp * rows_pad;
-    double* lfb = s.lf + (size_t)sp * rows_pad;
+    float* lfb = s.lf + (size_t)sp * rows_pad;
     for (int q = worker; q < Hs; q += nworkers) {
       const u32x4 r = philox4x32_10((uint32_t)q, t, spec, (uint32_t)(1 + sp), k0, k1);
-      const double u = u53(r.x, r.y);
-      const double zr = __dadd_rn(__dmul_rn(P.a - 1.0, u), 1.0);
-      const double zz = P.a_pow2 ? __dmul_rn(__dmul_rn(zr, zr), P.inv_a) : __ddiv_rn(__dmul_rn(zr, zr), P.a);
-      const double u2 = u53(r.w, (r.z << 16) | 0x8000u);
+      // the uniforms are assembled on the integer pipe (u53_int) and the accept threshold on the FP32 pipe: every
+      // FP64-pipe instruction of this phase would queue behind the co-resident CTA's tensor / DFMA stream
+      const double u = u53_int(r.x, r.y);
+      double zz;
+      if (a_is2) {                                    // ((a-1) u + 1)^2 / a with a = 2: (a-1) u = u and /2 are exact
+        const double zr = __dadd_rn(u, 1.0);
+        const double sq = __dmul_rn(zr, zr);          // in [1, 4): halving = one exponent step
+        zz = __hiloint2double(__double2hiint(sq) - 0x00100000, __double2loint(sq));
+      } else {
+        const double zr = __dadd_rn(__dmul_rn(P.a - 1.0, u), 1.0);
+        zz = P.a_pow2 ? __dmul_rn(__dmul_rn(zr, zr), P.inv_a) : __ddiv_rn(__dmul_rn(zr, zr), P.a);
+      }
+      const uint32_t zlow = (r.z << 16) | 0x8000u;
       zzb[q] = zz;
       s.partner[q] = (int)__umulhi(r.z, (uint32_t)Nc);
-      u2b[q] = u2;
-      // MUFU.LG2-based logarithms: |error| <= ~4e-6 here (zz in [1/a, a]; |ln u| <= 31 at 2^-22 relative), far
-      // inside the 2^-12 margin below which accept_filter() hands the decision to the FP64 logarithms
-      lfb[q] = (double)((float)(ndim - 1) * __logf((float)zz) - __logf((float)u2));
+      // FP32 image of (ndim-1) ln zz - ln u2 straight from the random words: |error| < 1e-5, far inside the 2^-12
+      // margin below which accept_filter() hands the decision to the FP64 logarithms
+      const float uf = (float)(r.x >> 8) * 5.9604644775390625e-08f;                    // 2^-24
+      const float zrf = fmaf(am1f, uf, 1.0f);
+      const float zzf = zrf * zrf * inv_af;
+      const float u2f = fmaf((float)(zlow >> 6), 1.1102230246251565e-16f,                // 2^-53
+                             (float)(r.w >> 5) * 7.450580596923828e-09f);              // 2^-27
+      lfb[q] = nd1f * __logf(zzf) - __logf(u2f);
     }
   };
 
@@ -660,8 +673,7 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
       const int off = sp ? H0 : 0, Hs = sp ? W - H0 : H0;
       const int coff = sp ? 0 : H0;
       const double* zzb = s.zz + (size_t)sp * rows_pad;
-      const double* u2b = s.u2 + (size_t)sp * rows_pad;
-      const double* lfb = s.lf + (size_t)sp * rows_pad;
+      const float* lfb = s.lf + (size_t)sp * rows_pad;
       // ---- PROPOSE: threads [0,Hs) build q = c_j - (c_j - s_k) zz (all random draws of this half-step were
       //      produced during the previous accept phase) -----------------------------------------------------
       FINE_START
@@ -693,11 +705,12 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
           // emcee: accept iff (ndim-1) ln zz + lp' - lp > ln u.  The logarithms were taken in FP32
           // (|error| < 1e-5): unless the margin is below the threshold the FP64 decision is already
           // determined; otherwise (about 1 proposal in 10^4) it is recomputed in FP64 as the oracle does.
-          const double est = __dsub_rn(lpn, lpo) + lfb[q];
+          const double est = __dsub_rn(lpn, lpo) + f32_widen_int(lfb[q]);
           bool accept;
           if (!accept_filter(est, lpn, lpo, accept)) {
+            const u32x4 r = philox4x32_10((uint32_t)q, t, spec, (uint32_t)(1 + sp), k0, k1);     // re-draw u2
             const double lnpdiff = __dsub_rn(__dadd_rn(__dmul_rn((double)(ndim - 1), log(zzb[q])), lpn), lpo);
-            accept = lnpdiff > log(u2b[q]);
+            accept = lnpdiff > log(u53_int(r.w, (r.z << 16) | 0x8000u));
           }
           if (accept) {
             copy_dims(s.coords + k * ndim, s.prop + q * ndim, ndim);

@@ -29,11 +29,10 @@ struct WpSmem {
   double* lp;       // [W]
   double* prop;     // [rows_pad][ndim]
   double* zz;       // [2][2][rows_pad]  stretch factors: [step parity][half-step][row]
-  double* u2;       // [2][2][rows_pad]  acceptance uniforms (FP64 fallback of the accept test)
   double* red;      // [8]
   long long* bkey;  // [2][ndim]
   double* bnd;      // [2][ndim]
-  float* lf;        // [2][2][rows_pad]  (ndim-1) ln zz - ln u2 in FP32 (accept filter)
+  float* lf;        // [2][2][rows_pad]  (ndim-1) ln zz - ln u2 in FP32 (accept filter); the rare FP64 fallback re-draws u2
   uint32_t* keys;   // [Wpad4]
   int* list;        // [2][W]            walker at rank, by step parity
   int* acc;         // [W]
@@ -46,7 +45,7 @@ __host__ __device__ inline int wp_rows_pad(int W) { return ceil_div((W + 1) / 2,
 
 __host__ __device__ inline size_t wp_smem_bytes(int W, int ndim) {
   const int rp = wp_rows_pad(W);
-  const size_t dbl = (size_t)W * ndim + W + (size_t)rp * ndim + 8 * (size_t)rp + 8 + 4 * (size_t)ndim;
+  const size_t dbl = (size_t)W * ndim + W + (size_t)rp * ndim + 4 * (size_t)rp + 8 + 4 * (size_t)ndim;
   const size_t words = 4 * (size_t)rp + (size_t)(W + 4) + 2 * W + W + 4 * rp + 2 * 260 + (W + 4);
   return dbl * 8 + words * 4 + 64;
 }
@@ -57,7 +56,6 @@ __device__ inline void wp_carve(WpSmem& s, double* base, int W, int ndim) {
   s.lp = base; base += W;
   s.prop = base; base += (size_t)rp * ndim;
   s.zz = base; base += 4 * rp;
-  s.u2 = base; base += 4 * rp;
   s.red = base; base += 8;
   s.bnd = base; base += 2 * ndim;
   s.bkey = reinterpret_cast<long long*>(base); base += 2 * ndim;
@@ -195,8 +193,9 @@ struct CollapsedMmaEvaluator {
   }
 };
 
-// Cole-Cole / Dias / Shin: two lanes per proposal, each over every second frequency (the loop body of vec_eval_chi).
-template <class Row>
+// Cole-Cole / Dias / Shin: two lanes per proposal, each over every second frequency (the loop body of vec_eval_chi),
+// ILP frequencies in flight per lane (their exp / reciprocal chains are latency-bound).
+template <class Row, int ILP = 2>
 struct VecWarpEvaluator {
   static constexpr bool kNeedsPrepare = true;
   VecSmem sm;
@@ -215,27 +214,28 @@ struct VecWarpEvaluator {
     constexpr int lpr = 2, stride = lpr * kFq;
     Row rr;
     rr.load(sm.rowc + (size_t)(row < nrows ? row : row0) * Row::kRC, n_modes);
-    double acc = 0.0, acc2 = 0.0;
+    double acc[ILP];
+#pragma unroll
+    for (int e = 0; e < ILP; ++e) acc[e] = 0.0;
     const double* f = sm.fq + sub * kFq;
     int j = row < nrows ? sub : N;                               // rows beyond the half-step: no work
-    for (; j + lpr < N; j += 2 * lpr, f += 2 * stride) {       // two frequencies in flight per lane
-      const double* f2 = f + stride;
-      double zre, zim, zre2, zim2;
-      const bool ok1 = rr.template eval<true>(f, zre, zim);
-      const bool ok2 = rr.template eval<true>(f2, zre2, zim2);
-      if (!(ok1 & ok2)) {                      // rare: a reciprocal left the fast path's range
-        rr.template eval<false>(f, zre, zim);
-        rr.template eval<false>(f2, zre2, zim2);
+    for (; j + (ILP - 1) * lpr < N; j += ILP * lpr, f += ILP * stride) {
+      double zre[ILP], zim[ILP];
+      bool ok = true;
+#pragma unroll
+      for (int e = 0; e < ILP; ++e) ok = ok & rr.template eval<true>(f + e * stride, zre[e], zim[e]);
+      if (!ok) {                               // rare: a reciprocal left the fast path's range
+#pragma unroll
+        for (int e = 0; e < ILP; ++e) rr.template eval<false>(f + e * stride, zre[e], zim[e]);
       }
-      const double2 a = lds2(f + 4), b = lds2(f + 6), a2 = lds2(f2 + 4), b2 = lds2(f2 + 6);
-      const double r0 = fma(-zre, a.y, a.x);
-      const double r1 = fma(-zim, b.y, b.x);
-      const double r2 = fma(-zre2, a2.y, a2.x);
-      const double r3 = fma(-zim2, b2.y, b2.x);
-      acc = fma(r0, r0, acc);
-      acc = fma(r1, r1, acc);
-      acc2 = fma(r2, r2, acc2);
-      acc2 = fma(r3, r3, acc2);
+#pragma unroll
+      for (int e = 0; e < ILP; ++e) {
+        const double2 a = lds2(f + e * stride + 4), b = lds2(f + e * stride + 6);
+        const double r0 = fma(-zre[e], a.y, a.x);     // (y - Z)/sigma
+        const double r1 = fma(-zim[e], b.y, b.x);
+        acc[e] = fma(r0, r0, acc[e]);
+        acc[e] = fma(r1, r1, acc[e]);
+      }
     }
     for (; j < N; j += lpr, f += stride) {
       double zre, zim;
@@ -243,20 +243,22 @@ struct VecWarpEvaluator {
       const double2 a = lds2(f + 4), b = lds2(f + 6);
       const double r0 = fma(-zre, a.y, a.x);
       const double r1 = fma(-zim, b.y, b.x);
-      acc = fma(r0, r0, acc);
-      acc = fma(r1, r1, acc);
+      acc[0] = fma(r0, r0, acc[0]);
+      acc[0] = fma(r1, r1, acc[0]);
     }
-    acc += acc2;
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    return acc;
+    double tot = acc[0];
+#pragma unroll
+    for (int e = 1; e < ILP; ++e) tot += acc[e];
+    tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+    return tot;
   }
 };
 
 // carve adaptors (the two evaluator families size their shared memory differently)
 template <int KS>
 __device__ __forceinline__ double* wp_eval_carve(CollapsedMmaEvaluator<KS>& ev, double* base, int) { return ev.carve(base); }
-template <class Row>
-__device__ __forceinline__ double* wp_eval_carve(VecWarpEvaluator<Row>& ev, double* base, int rp) { return ev.carve(base, rp); }
+template <class Row, int ILP>
+__device__ __forceinline__ double* wp_eval_carve(VecWarpEvaluator<Row, ILP>& ev, double* base, int rp) { return ev.carve(base, rp); }
 
 // q = c - (c - s) * zz for the dimensions d = sub, sub + 2, ... of one proposal (the two lanes of a row share it);
 // returns this lane's part of the strict-prior flag.  Fully unrolled per ndim like propose_and_check_n.
@@ -464,7 +466,6 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_wp_kernel(const EnsemblePar
     const int o = (((int)(t & 1u)) * 2 + sp) * rows_pad + q;
     s.zz[o] = zz;
     s.partner[o] = (int)__umulhi(rr.z, (uint32_t)Nc);
-    s.u2[o] = u53_int(rr.w, zlow);
     // FP32 image of (ndim-1) ln zz - ln u2 straight from the random words (no FP64 conversions): |error| < 1e-5,
     // far inside the 2^-12 margin below which accept_filter() hands the decision to the FP64 logarithms
     const float uf = (float)(rr.x >> 8) * 5.9604644775390625e-08f;                    // 2^-24
@@ -528,8 +529,9 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_wp_kernel(const EnsemblePar
           const double est = __dsub_rn(lpn, lpo) + f32_widen_int(s.lf[dq]);
           bool accept;
           if (!accept_filter(est, lpn, lpo, accept)) {
+            const u32x4 rr = philox4x32_10((uint32_t)q, t, spec, (uint32_t)(1 + sp), k0, k1);    // re-draw u2
             const double lnpdiff = __dsub_rn(__dadd_rn(__dmul_rn((double)(ndim - 1), log(s.zz[dq])), lpn), lpo);
-            accept = lnpdiff > log(s.u2[dq]);
+            accept = lnpdiff > log(u53_int(rr.w, (rr.z << 16) | 0x8000u));
           }
           if (accept) {
             copy_dims(s.coords + k * ndim, s.prop + q * ndim, ndim);
