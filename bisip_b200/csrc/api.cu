@@ -53,7 +53,7 @@ int check_desc(const bisip_model_desc* d) {
   switch (d->model) {
     case BISIP_MODEL_COLECOLE:
       if (d->n_modes < 1 || d->n_modes > kMaxModes)
-        return fail(BISIP_ERR_UNSUPPORTED, "ColeCole n_modes must be in [1,8]");
+        return fail(BISIP_ERR_UNSUPPORTED, "ColeCole n_modes must be in [1,16]");
       if (d->ndim != 1 + 3 * d->n_modes) return fail(BISIP_ERR_BAD_ARG, "ColeCole ndim != 1+3*n_modes");
       break;
     case BISIP_MODEL_DIAS:
@@ -65,8 +65,11 @@ int check_desc(const bisip_model_desc* d) {
     case BISIP_MODEL_DECOMP:
       if (d->n_tau <= 0 || d->n_coef <= 0) return fail(BISIP_ERR_BAD_ARG, "Decomp n_tau/n_coef must be positive");
       if (d->ndim != 1 + d->n_coef) return fail(BISIP_ERR_BAD_ARG, "Decomp ndim != 1+n_coef");
-      if (d->n_coef > 8 && !(d->precision == BISIP_PREC_FP64_COLLAPSED && d->n_coef <= 30))
-        return fail(BISIP_ERR_UNSUPPORTED, "Decomp poly_deg > 7 needs precision 'fp64-collapsed' (poly_deg <= 29)");
+      // poly_deg > 7: the two-stage tiles hold at most 8 coefficients; the FP64 precisions run the collapsed form
+      // (same 1e-12 parity) up to 30 coefficients, the TF32 modes have no such kernel
+      if (d->n_coef > 30) return fail(BISIP_ERR_UNSUPPORTED, "Decomp poly_deg > 29 not supported");
+      if (d->n_coef > 8 && d->precision != BISIP_PREC_FP64 && d->precision != BISIP_PREC_FP64_COLLAPSED)
+        return fail(BISIP_ERR_UNSUPPORTED, "Decomp poly_deg > 7 needs precision 'fp64' or 'fp64-collapsed'");
       if (d->precision < BISIP_PREC_FP64 || d->precision > BISIP_PREC_FP64_COLLAPSED)
         return fail(BISIP_ERR_BAD_ARG, "unknown precision");
       break;
@@ -100,7 +103,7 @@ int bisip_decomp_kernel_kind(const bisip_model_desc* desc, int n_walkers) {
   if (int rc = check_desc(desc)) return rc;
   if (desc->model != BISIP_MODEL_DECOMP || n_walkers < 2) return fail(BISIP_ERR_BAD_ARG, "bisip_decomp_kernel_kind: bad argument");
   const size_t other = sampler_smem_bytes(n_walkers, desc->ndim);
-  if (desc->precision == BISIP_PREC_FP64_COLLAPSED) return BISIP_KERNEL_FP64_COLLAPSED;
+  if (desc->precision == BISIP_PREC_FP64_COLLAPSED || desc->n_coef > 8) return BISIP_KERNEL_FP64_COLLAPSED;
   {
     const UmmaPlan up = plan_umma(*desc, other, (n_walkers + 1) / 2, true);
     if (up.ok) return up.cluster ? BISIP_KERNEL_TCGEN05_CLUSTER : BISIP_KERNEL_TCGEN05;
@@ -196,8 +199,11 @@ int bisip_ensemble_run(const bisip_model_desc* desc, int n_spectra, int n_walker
   {
     const char* e = getenv("BISIP_SAMPLER");
     const bool classic = e && !strcmp(e, "classic");
-    if (!classic && n_walkers <= 256) {
-      if (desc->model == BISIP_MODEL_DECOMP && desc->precision == BISIP_PREC_FP64_COLLAPSED && desc->n_coef <= 30)
+    const bool big_poly = desc->model == BISIP_MODEL_DECOMP && desc->n_coef > 8;     // FP64 on the collapsed tiles only
+    if (big_poly && n_walkers > 256)
+      return fail(BISIP_ERR_UNSUPPORTED, "Decomp poly_deg > 7 is sampled by the warp-private kernel: at most 256 walkers");
+    if ((!classic || big_poly) && n_walkers <= 256) {
+      if (desc->model == BISIP_MODEL_DECOMP && (desc->precision == BISIP_PREC_FP64_COLLAPSED || big_poly))
         return launch_ens_wp_collapsed(P, grid, st);
       // measured (profiles/r02_wp_sweep.md): warp-private wins by 1.2-2x for <= 64 walkers or short spectra and for
       // Cole-Cole everywhere; for Dias / Shin with > 64 walkers and > 32 frequencies the block-synchronous kernel is
@@ -287,7 +293,7 @@ int bisip_model_percentile(const bisip_model_desc* desc, int n_spectra, int64_t 
     // this kernel loops over modes / coefficients: the tile-shaped limits of the sampler kernels do not apply
     bisip_model_desc chk = d;
     if (chk.model == BISIP_MODEL_COLECOLE && chk.n_modes > kMaxModes) { chk.n_modes = 1; chk.ndim = 4; }
-    if (chk.model == BISIP_MODEL_DECOMP && chk.n_coef > 8) { chk.n_coef = 8; chk.ndim = 9; }
+    if (chk.model == BISIP_MODEL_DECOMP && chk.n_coef > 8) { chk.n_coef = 8; chk.ndim = 9; chk.precision = BISIP_PREC_FP64; }
     if (int rc = check_desc(&chk)) return rc;
     if (d.model == BISIP_MODEL_COLECOLE && (d.n_modes < 1 || d.ndim != 1 + 3 * d.n_modes))
       return fail(BISIP_ERR_BAD_ARG, "ColeCole ndim != 1+3*n_modes");

@@ -50,7 +50,9 @@ static int run_batch_vec_t(const BatchParams& P, cudaStream_t st) {
         case 2: return launch(vec_batch_kernel<ColeColeRowT<2>, WANT_Z>, grid, smem, st, "colecole_batch", &P);
         case 3: return launch(vec_batch_kernel<ColeColeRowT<3>, WANT_Z>, grid, smem, st, "colecole_batch", &P);
         case 4: return launch(vec_batch_kernel<ColeColeRowT<4>, WANT_Z>, grid, smem, st, "colecole_batch", &P);
-        default: return launch(vec_batch_kernel<ColeColeRow, WANT_Z>, grid, smem, st, "colecole_batch", &P);
+        default:
+          if (P.d.n_modes <= 8) return launch(vec_batch_kernel<ColeColeRow, WANT_Z>, grid, smem, st, "colecole_batch", &P);
+          return launch(vec_batch_kernel<ColeColeRowBig, WANT_Z>, grid, smem, st, "colecole_batch", &P);
       }
     case BISIP_MODEL_DIAS: return launch(vec_batch_kernel<DiasRow, WANT_Z>, grid, smem, st, "dias_batch", &P);
     default: return launch(vec_batch_kernel<ShinRow, WANT_Z>, grid, smem, st, "shin_batch", &P);

@@ -9,7 +9,9 @@ int launch_ens_colecole(const EnsembleParams& P, dim3 grid, size_t smem, cudaStr
     case 2: return launch_vec_ensemble<ColeColeRowT<2>, 6>(P, grid, smem, st, "ensemble_colecole");
     case 3: return launch(ensemble_kernel<VecEvaluator<ColeColeRowT<3>>, 2>, grid, smem, st, "ensemble_colecole", &P);
     case 4: return launch(ensemble_kernel<VecEvaluator<ColeColeRowT<4>>, 1>, grid, smem, st, "ensemble_colecole", &P);
-    default: return launch(ensemble_kernel<VecEvaluator<ColeColeRow>, 1>, grid, smem, st, "ensemble_colecole", &P);
+    default:
+      if (P.d.n_modes <= 8) return launch(ensemble_kernel<VecEvaluator<ColeColeRow>, 1>, grid, smem, st, "ensemble_colecole", &P);
+      return launch(ensemble_kernel<VecEvaluator<ColeColeRowBig>, 1>, grid, smem, st, "ensemble_colecole", &P);
   }
 }
 

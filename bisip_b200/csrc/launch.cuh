@@ -161,7 +161,7 @@ inline int vec_row_consts(const bisip_model_desc& d) {
         case 2: return ColeColeRowT<2>::kRC;
         case 3: return ColeColeRowT<3>::kRC;
         case 4: return ColeColeRowT<4>::kRC;
-        default: return ColeColeRow::kRC;
+        default: return d.n_modes <= 8 ? ColeColeRow::kRC : ColeColeRowBig::kRC;
       }
   }
 }

@@ -114,6 +114,71 @@ def test_collapsed_shape_sweep_chain_matches_oracle(N, W, T, kw):
     assert (np.max(np.abs(Z - Zo), axis=(1, 2)) / np.max(np.abs(Zo), axis=(1, 2))).max() <= 1e-12
 
 
+BIG_SHAPES = [
+    # model, N, W, T, kwargs — beyond the tile shapes of the two-stage kernels: poly_deg 8..12 (collapsed FP64 tiles with
+    # 2-4 k-steps, whatever FP64 precision is asked for) and 9..12 Cole-Cole modes (generic 16-mode kernel)
+    ('decomp', 20, 32, 40, dict(poly_deg=8, n_tau=40)),
+    ('decomp', 64, 64, 20, dict(poly_deg=9, n_tau=64)),
+    ('decomp', 33, 100, 15, dict(poly_deg=10, n_tau=50, c_exp=0.5)),
+    ('decomp', 64, 256, 8, dict(poly_deg=12, n_tau=128)),
+    ('decomp', 12, 60, 20, dict(poly_deg=14, n_tau=30)),
+    ('decomp', 20, 80, 10, dict(poly_deg=20, n_tau=40)),
+    ('colecole', 20, 64, 20, dict(n_modes=9)),
+    ('colecole', 33, 80, 12, dict(n_modes=12)),
+    ('colecole', 12, 100, 10, dict(n_modes=16)),
+]
+
+
+@pytest.mark.parametrize("model,N,W,T,kw", BIG_SHAPES, ids=[f"{s[0]}-N{s[1]}-W{s[2]}-{i}" for i, s in enumerate(BIG_SHAPES)])
+def test_unbounded_model_sizes_chain_forward_logprob(model, N, W, T, kw):
+    """The reference accepts any poly_deg (models.py:195, 207-208) and any n_modes (models.py:243-252).  Chain identical
+    to the oracle's on the same stream; batched forward / log-probability within 1e-12 of the oracle."""
+    from bisip_b200 import engine
+    from bisip_b200.batch import BatchInversion
+    from oracle import oracle
+    rng = np.random.default_rng(N * 1000 + W)
+    w, zn, ze, bounds, okw = _spectrum(model, N, rng, **kw)
+    inv = BatchInversion(model, w, zn[None], ze[None], nwalkers=W, nsteps=T, seed=99, spectrum_offset=7, **kw)
+    p0 = inv.draw_p0(0, 1)
+    res = inv.fit(p0=p0, keep_chain=True)
+    prob = oracle.Problem(model, w, zn, ze, bounds, **okw)
+    ref = prob.run(p0[0], T, seed=99, spectrum=7)
+    assert res['flags'][0] == 0 and not ref['nan']
+    np.testing.assert_array_equal(res['chain'][0], ref['chain'])
+    fin = np.isfinite(ref['log_prob'])
+    assert np.array_equal(fin, np.isfinite(res['log_prob'][0]))
+    assert np.max(np.abs(res['log_prob'][0][fin] - ref['log_prob'][fin]) / np.maximum(1, np.abs(ref['log_prob'][fin]))) <= 1e-12
+    th = np.concatenate([res['chain'][0][-1], p0[0][:7]])                 # posterior-ish and prior-wide thetas
+    dev_th, dev_w = inv._to_dev(th[None], 0, 1), inv._to_dev(w[None], 0, 1)[0]
+    Z = engine.forward(inv._spec(), dev_th, dev_w).cpu().numpy()[0]
+    Zo = prob.forward(th)
+    assert (np.max(np.abs(Z - Zo), axis=(1, 2)) / np.max(np.abs(Zo), axis=(1, 2))).max() <= 1e-12
+    lp = engine.log_probability(inv._spec(), dev_th, dev_w, inv._to_dev(zn[None], 0, 1), inv._to_dev(ze[None], 0, 1),
+                                inv._to_dev(bounds[None], 0, 1)[0]).cpu().numpy()[0]
+    lpo = prob.log_probability(th)
+    assert np.max(np.abs(lp - lpo) / np.maximum(1, np.abs(lpo))) <= 1e-12
+    # model percentiles (fused kernel) for the same sizes
+    mp = engine.model_percentile(inv._spec(), inv._to_dev(res['chain'][0][T // 2:].reshape(1, -1, th.shape[1]), 0, 1), dev_w, [50.0])
+    want = np.percentile(prob.forward(res['chain'][0][T // 2:].reshape(-1, th.shape[1])), 50.0, axis=0)
+    assert np.max(np.abs(mp.cpu().numpy()[0, 0] - want)) <= 1e-12 * np.max(np.abs(want))
+
+
+def test_big_polynomial_limits():
+    """poly_deg > 7 is an FP64-only, <= 256-walker path; beyond poly_deg 29 and for the TF32 modes the library says so."""
+    from bisip_b200 import _lib
+    from bisip_b200.batch import BatchInversion
+    w = 2 * np.pi * np.logspace(3, -1, 16)
+    zn, ze = np.zeros((1, 2, 16)), np.ones((1, 2, 16))
+    with pytest.raises(_lib.BisipError, match='256 walkers'):
+        BatchInversion('decomp', w, zn, ze, nwalkers=300, nsteps=3, poly_deg=9).fit()
+    with pytest.raises(_lib.BisipError, match='poly_deg > 29'):
+        BatchInversion('decomp', w, zn, ze, nwalkers=64, nsteps=3, poly_deg=30).fit()
+    with pytest.raises(_lib.BisipError, match="needs precision"):
+        BatchInversion('decomp', w, zn, ze, nwalkers=64, nsteps=3, poly_deg=9, precision='3xtf32').fit()
+    with pytest.raises(_lib.BisipError, match=r"\[1,16\]"):
+        BatchInversion('colecole', w, zn, ze, nwalkers=128, nsteps=3, n_modes=17).fit()
+
+
 def test_per_spectrum_grids_and_non_pow2_scale():
     """w (B,N) and the tau grids differ per spectrum (w_stride / tau_stride paths); a = 2.5 takes the
     true-division branch of the stretch factor."""
@@ -183,9 +248,11 @@ def test_c_abi_argument_errors():
     d = _lib.ModelDesc(_lib.MODEL_DIAS, 4, 8, 1, 0, 0, 0, 0, 1.0)                  # Dias with ndim 4
     assert lib.bisip_forward(C.byref(d), 1, 1, None, None, 0, None, None, 0, None, None) == -1
     assert b"ndim" in lib.bisip_last_error()
-    d = _lib.ModelDesc(_lib.MODEL_DECOMP, 10, 8, 1, 16, 9, 0, 0, 1.0)               # poly_deg 8
+    d = _lib.ModelDesc(_lib.MODEL_DECOMP, 32, 8, 1, 16, 31, 0, 0, 1.0)              # poly_deg 30
     assert lib.bisip_forward(C.byref(d), 1, 1, None, None, 0, None, None, 0, None, None) == -2
-    d = _lib.ModelDesc(_lib.MODEL_COLECOLE, 28, 8, 9, 0, 0, 0, 0, 1.0)              # 9 modes
+    d = _lib.ModelDesc(_lib.MODEL_DECOMP, 10, 8, 1, 16, 9, _lib.PREC_3XTF32, 0, 1.0)  # poly_deg 8 in a TF32 mode
+    assert lib.bisip_forward(C.byref(d), 1, 1, None, None, 0, None, None, 0, None, None) == -2
+    d = _lib.ModelDesc(_lib.MODEL_COLECOLE, 52, 8, 17, 0, 0, 0, 0, 1.0)             # 17 modes
     assert lib.bisip_forward(C.byref(d), 1, 1, None, None, 0, None, None, 0, None, None) == -2
     d = _lib.ModelDesc(_lib.MODEL_DIAS, 5, 8, 1, 0, 0, 0, 0, 1.0)
     assert lib.bisip_forward(C.byref(d), 0, 1, None, None, 0, None, None, 0, None, None) == -1   # empty batch
