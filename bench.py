@@ -276,6 +276,21 @@ def _dev(torch, a, dev):
     return torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64))).to(dev)
 
 
+def vec_roofline(fl, name, evals_per_s, peak_dfma):
+    """FP64-pipe roofline of a vector-model kernel from the executed FP64 instruction counts ncu measured once
+    (profiles/ncu_summary.json: fp64_flop_per_eval).  `frac` = executed FP64 thread instructions per second over the
+    pipe's instruction rate (peak DFMA flops / 2: a DMUL or DADD occupies the same slot as a DFMA) — the utilisation
+    figure north_star's 50 % bar is about; `achieved` (flops, FMA = 2) is given next to it."""
+    d = fl.get("detail", {}).get(name)
+    if not d:
+        return None
+    inst_rate = evals_per_s * d["fp64_inst_per_eval"]
+    return {"bound": "fp64 pipe", "fp64_flop_per_eval": d["flop_per_eval"], "fp64_inst_per_eval": d["fp64_inst_per_eval"],
+            "achieved": evals_per_s * d["flop_per_eval"] / 1e12, "peak": peak_dfma, "unit": "TFLOP/s",
+            "frac": inst_rate / (peak_dfma * 1e12 / 2.0), "frac_in_flops": evals_per_s * d["flop_per_eval"] / 1e12 / peak_dfma,
+            "ncu_fp64_pipe_pct_of_active_cycles": d.get("fp64_pipe_pct_active"), "flop_source": fl.get("source")}
+
+
 def run_other_configs(torch, engine, synthetic, BatchInversion, _lib, dev, peak_dmma, peak_dfma):
     """BASELINE configs 2-4 on one GPU (config 1 is the reference's own CPU-sized case; config 5 is the headline)."""
     out = {}
@@ -294,10 +309,7 @@ def run_other_configs(torch, engine, synthetic, BatchInversion, _lib, dev, peak_
         syn = synthetic.make(model, 0, 1024, fwd_for(model), N=N_FREQ)
         inv = BatchInversion(model, w, pin(syn['zn']), pin(syn['zn_err']), nwalkers=128, nsteps=2000, seed=SEED, device=dev)
         r = measure_config(torch, engine, inv, pin(inv.draw_p0(0, 1024)), DISCARD, THIN)
-        fpe = fl.get(f"ensemble_{model}")
-        r["roofline"] = ({"bound": "fp64 pipe", "fp64_flop_per_eval": fpe, "achieved": r["evals_per_s"] * fpe / 1e12,
-                          "peak": peak_dfma, "unit": "TFLOP/s", "frac": r["evals_per_s"] * fpe / 1e12 / peak_dfma,
-                          "flop_source": fl.get("source")} if fpe else None)
+        r["roofline"] = vec_roofline(fl, f"ensemble_{model}", r["evals_per_s"], peak_dfma)
         out[f"C3_{model}"] = dict(workload=f"{model}: 1,024 synthetic {N_FREQ}-frequency spectra, 128 walkers x 2000 steps", **r)
     # ---- C2: ColeCole n_modes=2 on the bundled example spectrum, 64 walkers x 2000 steps, batched x 1,024 streams
     from bisip_b200.data import example_tables
@@ -306,9 +318,7 @@ def run_other_configs(torch, engine, synthetic, BatchInversion, _lib, dev, peak_
     inv = BatchInversion('colecole', d['w'], pin(np.repeat(d['zn'][None], 1024, 0)), pin(np.repeat(d['zn_err'][None], 1024, 0)),
                          nwalkers=64, nsteps=2000, n_modes=2, seed=SEED, device=dev)
     r = measure_config(torch, engine, inv, pin(inv.draw_p0(0, 1024)), DISCARD, THIN)
-    fpe = fl.get("ensemble_colecole2_n20")
-    r["roofline"] = ({"bound": "fp64 pipe", "fp64_flop_per_eval": fpe, "achieved": r["evals_per_s"] * fpe / 1e12, "peak": peak_dfma,
-                      "unit": "TFLOP/s", "frac": r["evals_per_s"] * fpe / 1e12 / peak_dfma, "flop_source": fl.get("source")} if fpe else None)
+    r["roofline"] = vec_roofline(fl, "ensemble_colecole2_n20", r["evals_per_s"], peak_dfma)
     out["C2_colecole2"] = dict(workload="ColeCole n_modes=2, bundled SIP-K389175 (20 frequencies), 64 walkers x 2000 steps, "
                                         "1,024 independent streams of the same spectrum in one launch", **r)
     # ---- C4: decomposition with 256 taus, 10,000 synthetic spectra, 256 walkers x 2000 steps: FP64 DMMA vs TF32 / 3xTF32 / collapsed

@@ -149,7 +149,11 @@ def main():
                     f"{g['stall_barrier']} | {g['stall_math']} | {g['stall_wait']} | {g['stall_short_sb']} |\n")
     summ_path = os.path.join(os.path.dirname(a.out), "ncu_summary.json")
     summ = json.load(open(summ_path)) if os.path.exists(summ_path) else {}
+    keep = {k: summ.get(a.name, {}).get(k) for k in ("dram_bytes_per_launch_at_bench_size", "dram_bytes_source", "kernel_sources_sha")}
     summ[a.name] = {k: v for k, v in m.items() if k != "regions"}
+    for k, v in keep.items():          # bench-size DRAM figure and the source hash it belongs to (bench.py quotes it only while they match)
+        if v is not None and k not in summ[a.name]:
+            summ[a.name][k] = v
     json.dump(summ, open(summ_path, "w"), indent=1)
     print(json.dumps({k: v for k, v in m.items() if k != "regions"}, indent=1))
 
