@@ -10,7 +10,7 @@ all: $(LIB) tools/peaks oracle
 
 # One object per kernel family so that they compile in parallel (`make -j`); no device code crosses a
 # translation unit, so a plain host link is enough.  ptxas -v output of every unit is kept in $(CSRC)/ptxas.log.
-UNITS     := api ens_wp_collapsed ens_wp_vec ens_dmma ens_rc ens_umma ens_collapsed ens_colecole ens_dias_shin batch_decomp batch_vec
+UNITS     := api ens_wp_collapsed ens_wp_vec ens_wp_dmma ens_dmma ens_rc ens_umma ens_collapsed ens_colecole ens_dias_shin batch_decomp batch_vec
 OBJS      := $(UNITS:%=$(CSRC)/%.o)
 
 $(CSRC)/%.o: $(CSRC)/%.cu $(HDRS)

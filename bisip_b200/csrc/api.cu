@@ -205,6 +205,8 @@ int bisip_ensemble_run(const bisip_model_desc* desc, int n_spectra, int n_walker
     if ((!classic || big_poly) && n_walkers <= 256) {
       if (desc->model == BISIP_MODEL_DECOMP && (desc->precision == BISIP_PREC_FP64_COLLAPSED || big_poly))
         return launch_ens_wp_collapsed(P, grid, st);
+      if (desc->model == BISIP_MODEL_DECOMP && desc->precision == BISIP_PREC_FP64 && desc->n_tau > 32 && desc->n_tau <= 64)
+        return launch_ens_wp_dmma(P, grid, st);
       // measured (profiles/r02_wp_sweep.md): warp-private wins by 1.2-2x for <= 64 walkers or short spectra and for
       // Cole-Cole everywhere; for Dias / Shin with > 64 walkers and > 32 frequencies the block-synchronous kernel is
       // 2-6 % faster (its serial phases run on full warps; the long frequency loop dominates either way)

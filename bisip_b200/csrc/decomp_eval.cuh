@@ -78,11 +78,11 @@ __device__ inline void decomp_init(DecompSmem& s, const DecompShape& sh, double 
                                    const double* __restrict__ log_taus,
                                    const double* __restrict__ y, const double* __restrict__ yerr,
                                    double* red) {
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nthr = blockDim.x;     // any CTA size (the warp-private sampler runs 32 ... 256 threads)
   const int N = sh.N, S = sh.S, KC = sh.KC;
-  for (int i = tid; i < (int)sh.kf_doubles(); i += kThreads) s.Kf[i] = 0.0;
+  for (int i = tid; i < (int)sh.kf_doubles(); i += nthr) s.Kf[i] = 0.0;
   // stage-1 B fragments: tile j (8 taus), half q: power t+4q, tau 8j+g
-  for (int i = tid; i < (int)sh.l1_doubles(); i += kThreads) {
+  for (int i = tid; i < (int)sh.l1_doubles(); i += nthr) {
     const int lane = i & 31, q = (i >> 5) & 1, j = i >> 6;
     const int g = lane >> 2, t = lane & 3;
     const int p = t + 4 * q, k = 8 * j + g;
@@ -93,7 +93,7 @@ __device__ inline void decomp_init(DecompSmem& s, const DecompShape& sh, double 
   // so K is stored pre-scaled by 1/sigma_c and the accumulators start at ys_c - R0*ds_c.
   const bool scaled = (y != nullptr);
   double csum = 0.0;
-  for (int c = tid; c < (int)sh.col_doubles(); c += kThreads) {
+  for (int c = tid; c < (int)sh.col_doubles(); c += nthr) {
     double ys = 0.0, ds = 0.0;
     if (c < 2 * N && scaled) {
       const double e = yerr[c];
@@ -108,7 +108,7 @@ __device__ inline void decomp_init(DecompSmem& s, const DecompShape& sh, double 
   __syncthreads();   // Kf zero-fill complete before scatter
   double cs, sn;
   sincospi(0.5 * c_exp, &sn, &cs);
-  for (int i = tid; i < S * N; i += kThreads) {
+  for (int i = tid; i < S * N; i += nthr) {
     const int k = i / N, j = i - k * N;
     double kre, kim;
     debye_kernel_term(w[j], taus[k], c_exp, cs, sn, kre, kim);
@@ -125,7 +125,7 @@ __device__ inline void decomp_init(DecompSmem& s, const DecompShape& sh, double 
   if ((tid & 31) == 0) red[tid >> 5] = csum;
   __syncthreads();
   double tot = 0.0;
-  for (int i = 0; i < kWarps; ++i) tot += red[i];
+  for (int i = 0; i < (nthr >> 5); ++i) tot += red[i];
   s.llconst = tot;
   __syncthreads();
 }

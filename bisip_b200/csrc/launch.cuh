@@ -174,6 +174,7 @@ int launch_ens_collapsed(const EnsembleParams& P, dim3 grid, size_t smem, cudaSt
 int launch_ens_colecole(const EnsembleParams& P, dim3 grid, size_t smem, cudaStream_t st);                   // ens_colecole.cu
 int launch_ens_dias_shin(const EnsembleParams& P, dim3 grid, size_t smem, cudaStream_t st);                  // ens_dias_shin.cu
 int launch_ens_wp_collapsed(const EnsembleParams& P, dim3 grid, cudaStream_t st);                            // ens_wp_collapsed.cu
+int launch_ens_wp_dmma(const EnsembleParams& P, dim3 grid, cudaStream_t st);                                 // ens_wp_dmma.cu
 int launch_ens_wp_vec(const EnsembleParams& P, dim3 grid, cudaStream_t st);                                  // ens_wp_vec.cu
 int run_batch_decomp(const BatchParams& P, bool want_z, cudaStream_t st);                                    // batch_decomp.cu
 int run_batch_vec(const BatchParams& P, bool want_z, cudaStream_t st);                                       // batch_vec.cu

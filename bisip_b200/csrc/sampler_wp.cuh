@@ -193,6 +193,71 @@ struct CollapsedMmaEvaluator {
   }
 };
 
+// The default two-stage contraction on FP64 tensor tiles (decomp_eval.cuh), one 16-proposal row tile per warp: stage 1
+// leaves the chargeability in accumulator layout = the stage-2 A fragment, stage 2 streams the fragment-ordered kernel
+// matrix, the epilogue squares the residuals on the accumulators.  The same instructions as decomp_eval_chi, without
+// the shared-memory round trip of chi^2 and without CTA barriers around the evaluation.
+template <int KC>
+struct DecompMmaWarpEvaluator {
+  static constexpr bool kNeedsPrepare = false;
+  DecompSmem sm;
+  DecompShape sh;
+  __device__ DecompMmaWarpEvaluator(const bisip_model_desc& d) : sh(d.n_freq, d.n_tau, d.n_coef) {}
+  static __host__ size_t smem_doubles(const bisip_model_desc& d) {
+    const DecompShape h(d.n_freq, d.n_tau, d.n_coef);
+    return h.kf_doubles() + h.l1_doubles() + 2 * h.col_doubles();
+  }
+  __device__ double* carve(double* base) {
+    sm.Kf = base; base += sh.kf_doubles();
+    sm.L1 = base; base += sh.l1_doubles();
+    sm.ycol = base; base += sh.col_doubles();
+    sm.isig = base; base += sh.col_doubles();
+    sm.part = nullptr;
+    return base;
+  }
+  __device__ void init(const bisip_model_desc& d, const double* w, const double* taus, const double* log_taus,
+                       const double* y, const double* yerr, double* red) {
+    decomp_init(sm, sh, d.c_exp, w, taus, log_taus, y, yerr, red);
+  }
+  __device__ double llconst() const { return sm.llconst; }
+  __device__ __forceinline__ void prepare_row(int, const double*) {}
+  __device__ __forceinline__ double eval_warp(const double* __restrict__ prop, int ndim, int row0, int, int lane) const {
+    const int t = lane & 3;
+    double A[KC][8];
+    double R0a, R0b;
+    decomp_stage1<KC>(sm, sh.D, prop, ndim, row0 >> 4, lane, A, R0a, R0b);
+    double chi_lo = 0.0, chi_hi = 0.0;
+#pragma unroll 2
+    for (int nt = 0; nt < sh.NT2; ++nt) {
+      const int col = nt * 8 + 2 * t;
+      const double2 ys = *reinterpret_cast<const double2*>(sm.ycol + col);
+      double c[4];
+      if (nt * 8 >= sh.N) {          // tile entirely in the imaginary block: delta = 0 (warp-uniform)
+        c[0] = ys.x; c[1] = ys.y; c[2] = ys.x; c[3] = ys.y;
+      } else {
+        const double2 ds = *reinterpret_cast<const double2*>(sm.isig + col);
+        c[0] = fma(-R0a, ds.x, ys.x);
+        c[1] = fma(-R0a, ds.y, ys.y);
+        c[2] = fma(-R0b, ds.x, ys.x);
+        c[3] = fma(-R0b, ds.y, ys.y);
+      }
+      decomp_stage2_tile<KC>(sm, nt, lane, A, c);      // c = (y - Z)/sigma
+      chi_lo = fma(c[0], c[0], chi_lo);
+      chi_lo = fma(c[1], c[1], chi_lo);
+      chi_hi = fma(c[2], c[2], chi_hi);
+      chi_hi = fma(c[3], c[3], chi_hi);
+    }
+    chi_lo += __shfl_xor_sync(0xffffffffu, chi_lo, 1);
+    chi_lo += __shfl_xor_sync(0xffffffffu, chi_lo, 2);
+    chi_hi += __shfl_xor_sync(0xffffffffu, chi_hi, 1);
+    chi_hi += __shfl_xor_sync(0xffffffffu, chi_hi, 2);
+    const int r = lane >> 1;
+    const double lo = __shfl_sync(0xffffffffu, chi_lo, 4 * (r & 7));
+    const double hi = __shfl_sync(0xffffffffu, chi_hi, 4 * (r & 7));
+    return (r >> 3) ? hi : lo;
+  }
+};
+
 // Cole-Cole / Dias / Shin: two lanes per proposal, each over every second frequency (the loop body of vec_eval_chi),
 // ILP frequencies in flight per lane (their exp / reciprocal chains are latency-bound).
 template <class Row, int ILP = 2>
@@ -259,6 +324,8 @@ template <int KS>
 __device__ __forceinline__ double* wp_eval_carve(CollapsedMmaEvaluator<KS>& ev, double* base, int) { return ev.carve(base); }
 template <class Row, int ILP>
 __device__ __forceinline__ double* wp_eval_carve(VecWarpEvaluator<Row, ILP>& ev, double* base, int rp) { return ev.carve(base, rp); }
+template <int KC>
+__device__ __forceinline__ double* wp_eval_carve(DecompMmaWarpEvaluator<KC>& ev, double* base, int) { return ev.carve(base); }
 
 // q = c - (c - s) * zz for the dimensions d = sub, sub + 2, ... of one proposal (the two lanes of a row share it);
 // returns this lane's part of the strict-prior flag.  Fully unrolled per ndim like propose_and_check_n.
