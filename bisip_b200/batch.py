@@ -230,15 +230,23 @@ class BatchInversion:
             return a[lo:hi].to(self.device, dtype=torch.float64, non_blocking=True).contiguous()
         return _lib.dev_f64(a[lo:hi], self.device)
 
+    P0_BLOCK = 64
+
     def draw_p0(self, lo, hi):
         """Uniform starting positions inside the bounds, like ``Inversion.fit`` does with
-        ``np.random.uniform`` (reference ``models.py:104-106``), drawn per spectrum from
-        ``default_rng(seed + global_index)`` so they do not depend on sharding."""
+        ``np.random.uniform`` (reference ``models.py:104-106``).  Spectra are drawn in blocks of 64 global indices
+        from ``default_rng([seed, block])`` (one generator per block, not per spectrum: a 100,000-spectra survey
+        needs 1,563 of them), so the positions of a spectrum depend on its global index only — not on sharding or
+        sub-batching."""
         out = np.empty((hi - lo, self.nwalkers, self.ndim))
         lob, hib = self.param_bounds
-        for i in range(lo, hi):
-            rng = np.random.default_rng([self.seed, self.spectrum_offset + i])
-            out[i - lo] = rng.uniform(lob, hib, (self.nwalkers, self.ndim))
+        g0, g1 = self.spectrum_offset + lo, self.spectrum_offset + hi
+        nb = self.P0_BLOCK
+        for blk in range(g0 // nb, (g1 + nb - 1) // nb):
+            rng = np.random.default_rng([self.seed, blk])
+            block = rng.uniform(lob, hib, (nb, self.nwalkers, self.ndim))
+            a, b = max(g0, blk * nb), min(g1, (blk + 1) * nb)
+            out[a - g0:b - g0] = block[a - blk * nb:b - blk * nb]
         return out
 
     def _validate(self, p0):

@@ -213,6 +213,54 @@ __device__ __forceinline__ void copy_dims(double* __restrict__ dst, const double
   for (int d = kDimUnroll; d < ndim; ++d) dst[d] = src[d];
 }
 
+// All random draws of proposal rows of half-step (t, sp) from one Philox call per proposal (stream layout at the top of
+// this file): stretch factor, partner index, and the FP32 image of the accept threshold (ndim-1) ln zz - ln u2.  It only
+// depends on the Philox counter, so it may run anywhere before the next PROPOSE phase (the sampler gives it to the
+// threads that have no proposal to accept).
+struct DrawCtx {
+  double* zz;          // [2][rows_pad]
+  float* lf;           // [2][rows_pad]
+  int* partner;        // [rows_pad]
+  int rows_pad, W, H0, ndim;
+  uint32_t spec, k0, k1;
+  double a, inv_a;
+  int a_pow2;
+};
+
+__device__ __forceinline__ void draw_rows(const DrawCtx& c, uint32_t t, int sp, int worker, int nworkers) {
+  const int Hs = sp ? c.W - c.H0 : c.H0, Nc = c.W - Hs;
+  double* zzb = c.zz + (size_t)sp * c.rows_pad;
+  float* lfb = c.lf + (size_t)sp * c.rows_pad;
+  const bool a_is2 = c.a == 2.0;
+  const float am1f = (float)(c.a - 1.0), inv_af = (float)c.inv_a, nd1f = (float)(c.ndim - 1);
+  for (int q = worker; q < Hs; q += nworkers) {
+    const u32x4 r = philox4x32_10((uint32_t)q, t, c.spec, (uint32_t)(1 + sp), c.k0, c.k1);
+    // the uniforms are assembled on the integer pipe (u53_int) and the accept threshold on the FP32 pipe: every
+    // FP64-pipe instruction of this work would queue behind the co-resident warps' tensor / DFMA stream
+    const double u = u53_int(r.x, r.y);
+    double zz;
+    if (a_is2) {                                    // ((a-1) u + 1)^2 / a with a = 2: (a-1) u = u and /2 are exact
+      const double zr = __dadd_rn(u, 1.0);
+      const double sq = __dmul_rn(zr, zr);          // in [1, 4): halving = one exponent step
+      zz = __hiloint2double(__double2hiint(sq) - 0x00100000, __double2loint(sq));
+    } else {
+      const double zr = __dadd_rn(__dmul_rn(c.a - 1.0, u), 1.0);
+      zz = c.a_pow2 ? __dmul_rn(__dmul_rn(zr, zr), c.inv_a) : __ddiv_rn(__dmul_rn(zr, zr), c.a);
+    }
+    const uint32_t zlow = (r.z << 16) | 0x8000u;
+    zzb[q] = zz;
+    c.partner[q] = (int)__umulhi(r.z, (uint32_t)Nc);
+    // FP32 image of (ndim-1) ln zz - ln u2 straight from the random words: |error| < 1e-5, far inside the 2^-12
+    // margin below which accept_filter() hands the decision to the FP64 logarithms
+    const float uf = (float)(r.x >> 8) * 5.9604644775390625e-08f;                    // 2^-24
+    const float zrf = fmaf(am1f, uf, 1.0f);
+    const float zzf = zrf * zrf * inv_af;
+    const float u2f = fmaf((float)(zlow >> 6), 1.1102230246251565e-16f,                // 2^-53
+                           (float)(r.w >> 5) * 7.450580596923828e-09f);              // 2^-27
+    lfb[q] = nd1f * __logf(zzf) - __logf(u2f);
+  }
+}
+
 // Side work executed INSIDE the evaluation phase: ranking the shuffle keys of the next step.  It is
 // pure integer/LDS work, so it fills issue slots that the tile loop leaves idle while its warps wait
 // for the FP64 tensor pipe; the evaluators call advance() once per column-tile iteration.
@@ -325,6 +373,66 @@ __device__ __forceinline__ void rank_keys_binned(const uint32_t* __restrict__ ke
   __syncthreads();
   if (tid < W) {
     const int end = hist[bin + 1];
+    int cnt = 0;
+    for (int j = start; j < end; ++j) cnt += sorted[j] < key ? 1 : 0;
+    list_out[start + cnt] = tid;
+  }
+}
+
+// Binned key ranking (rank_keys_binned of sampler.cuh) cut at its barriers so that the sampler can place the pieces
+// between the barriers it has anyway.  `hist` must be zero on entry of part A.
+//   A  slot of every key inside its bin                       (needs: keys visible)          -> returns (key, bin, slot)
+//   -- barrier --
+//   B  every warp scans the 256 bin counts itself and writes the SAME starts (benign identical stores), then places
+//      its keys:  sorted[start + slot] = key
+//   -- barrier --
+//   C  rank = start + smaller keys in the own bin ; list_out[rank] = walker
+template <int NT>
+__device__ __forceinline__ void rank_part_a(const uint32_t* __restrict__ keys, int W, int* __restrict__ hist,
+                                            uint32_t& key, int& bin, int& slot) {
+  const int tid = threadIdx.x;
+  key = 0; bin = 0; slot = 0;
+  if (tid < W) {
+    key = keys[tid];
+    bin = (int)(key >> 24);
+    slot = atomicAdd(&hist[bin], 1);
+  }
+}
+template <int NT>
+__device__ __forceinline__ int rank_part_b(int W, int* __restrict__ hist, int* __restrict__ starts, uint32_t* __restrict__ sorted,
+                                           uint32_t key, int bin, int slot) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  {                                                // exclusive scan of the 256 counters, 8 per lane, by every warp
+    const int4* h4 = reinterpret_cast<const int4*>(hist);
+    const int4 a = h4[2 * lane], c = h4[2 * lane + 1];
+    const int s0 = a.x, s1 = s0 + a.y, s2 = s1 + a.z, s3 = s2 + a.w, s4 = s3 + c.x, s5 = s4 + c.y, s6 = s5 + c.z;
+    const int tot = s6 + c.w;
+    int inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += n;
+    }
+    const int base = inc - tot;
+    int4* o4 = reinterpret_cast<int4*>(starts);
+    o4[2 * lane] = make_int4(base, base + s0, base + s1, base + s2);
+    o4[2 * lane + 1] = make_int4(base + s3, base + s4, base + s5, base + s6);
+    if (lane == 31) starts[256] = inc;
+  }
+  __syncwarp();
+  int start = 0;
+  if (tid < W) {
+    start = starts[bin];
+    sorted[start + slot] = key;
+  }
+  return start;
+}
+template <int NT>
+__device__ __forceinline__ void rank_part_c(int W, const int* __restrict__ starts, const uint32_t* __restrict__ sorted,
+                                            int* __restrict__ list_out, uint32_t key, int bin, int start) {
+  const int tid = threadIdx.x;
+  if (tid < W) {
+    const int end = starts[bin + 1];
     int cnt = 0;
     for (int j = start; j < end; ++j) cnt += sorted[j] < key ? 1 : 0;
     list_out[start + cnt] = tid;
@@ -601,8 +709,6 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
   const int Wpad4 = (W + 3) & ~3;
   int kept = 0;
 
-  const bool a_is2 = P.a == 2.0;
-  const float am1f = (float)(P.a - 1.0), inv_af = (float)P.inv_a, nd1f = (float)(ndim - 1);
   // ---- work that depends only on the Philox stream runs one phase AHEAD of its use, on threads that
   //      would otherwise idle, so that the serial phases between two evaluations stay short ----------
   // shuffle keys of step t (emcee: shuffle(arange(W) % 2)): one Philox call feeds 4 walkers
@@ -617,50 +723,21 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
       }
     }
   };
-  // all draws of half-step (t, sp) from one Philox call per proposal: stretch factor zz, partner index, acceptance
-  // uniform u2 and the FP32 image of the accept threshold
-  auto gen_proposal_draws = [&](uint32_t t, int sp, int worker, int nworkers) {
-    const int Hs = sp ? W - H0 : H0, Nc = W - Hs;
-    double* zzb = s.zz + (size_t)sp * rows_pad;
-    float* lfb = s.lf + (size_t)sp * rows_pad;
-    for (int q = worker; q < Hs; q += nworkers) {
-      const u32x4 r = philox4x32_10((uint32_t)q, t, spec, (uint32_t)(1 + sp), k0, k1);
-      // the uniforms are assembled on the integer pipe (u53_int) and the accept threshold on the FP32 pipe: every
-      // FP64-pipe instruction of this phase would queue behind the co-resident CTA's tensor / DFMA stream
-      const double u = u53_int(r.x, r.y);
-      double zz;
-      if (a_is2) {                                    // ((a-1) u + 1)^2 / a with a = 2: (a-1) u = u and /2 are exact
-        const double zr = __dadd_rn(u, 1.0);
-        const double sq = __dmul_rn(zr, zr);          // in [1, 4): halving = one exponent step
-        zz = __hiloint2double(__double2hiint(sq) - 0x00100000, __double2loint(sq));
-      } else {
-        const double zr = __dadd_rn(__dmul_rn(P.a - 1.0, u), 1.0);
-        zz = P.a_pow2 ? __dmul_rn(__dmul_rn(zr, zr), P.inv_a) : __ddiv_rn(__dmul_rn(zr, zr), P.a);
-      }
-      const uint32_t zlow = (r.z << 16) | 0x8000u;
-      zzb[q] = zz;
-      s.partner[q] = (int)__umulhi(r.z, (uint32_t)Nc);
-      // FP32 image of (ndim-1) ln zz - ln u2 straight from the random words: |error| < 1e-5, far inside the 2^-12
-      // margin below which accept_filter() hands the decision to the FP64 logarithms
-      const float uf = (float)(r.x >> 8) * 5.9604644775390625e-08f;                    // 2^-24
-      const float zrf = fmaf(am1f, uf, 1.0f);
-      const float zzf = zrf * zrf * inv_af;
-      const float u2f = fmaf((float)(zlow >> 6), 1.1102230246251565e-16f,                // 2^-53
-                             (float)(r.w >> 5) * 7.450580596923828e-09f);              // 2^-27
-      lfb[q] = nd1f * __logf(zzf) - __logf(u2f);
-    }
-  };
+  DrawCtx dctx;
+  dctx.zz = s.zz; dctx.lf = s.lf; dctx.partner = s.partner; dctx.rows_pad = rows_pad; dctx.W = W; dctx.H0 = H0; dctx.ndim = ndim;
+  dctx.spec = spec; dctx.k0 = k0; dctx.k1 = k1; dctx.a = P.a; dctx.inv_a = P.inv_a; dctx.a_pow2 = P.a_pow2;
+  const bool binned = W <= NT;                       // binned ranking (one key per thread); else the all-pairs side work
 
   // prologue: split of step 0 and the draws of its first half-step
   gen_keys((uint32_t)P.step0, tid, NT);
   __syncthreads();
-  if (W <= NT) {
+  if (binned) {
     rank_keys_binned<NT>(s.keys, s.list, W, s.hist, s.sorted);
   } else {
     side.begin(s.keys, s.list, W, 0);
     side.finish();
   }
-  gen_proposal_draws((uint32_t)P.step0, 0, tid, NT);
+  draw_rows(dctx, (uint32_t)P.step0, 0, tid, NT);
   __syncthreads();
 
   PHASE_DECL
@@ -674,8 +751,9 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
       const int coff = sp ? 0 : H0;
       const double* zzb = s.zz + (size_t)sp * rows_pad;
       const float* lfb = s.lf + (size_t)sp * rows_pad;
-      // ---- PROPOSE: threads [0,Hs) build q = c_j - (c_j - s_k) zz (all random draws of this half-step were
-      //      produced during the previous accept phase) -----------------------------------------------------
+      // ---- PROPOSE: threads [0,Hs) build q = c_j - (c_j - s_k) zz (the random draws of this half-step were produced
+      //      under the previous evaluation).  Second half-step: every thread also takes the bin slot of its key of the
+      //      NEXT step's split (keys drawn in the first accept phase) — the ranking rides on the barriers that exist ----
       FINE_START
       for (int q = tid; q < Hs; q += NT) {
         const int j = list[coff + s.partner[q]];
@@ -693,54 +771,55 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
       __syncthreads();
       FINE_MARK(9)
       PHASE_MARK(2)
-      // ---- ACCEPT (threads [0,Hs)) ; the other threads draw the proposal factors of the next
-      //      half-step, and after the first half-step the first threads also draw the next step's keys --------
-      for (int idx = tid; idx < 2 * Hs; idx += NT) {
-        if (idx < Hs) {
-          const int q = idx;
-          const int k = list[off + q];
-          const double lpo = s.lp[k];
-          const double lpn = s.inb[q] ? -0.5 * (ev.chi_of(s.chi, q) + llc) : neg_inf();
-          if (lpn != lpn) flag |= 1;
-          // emcee: accept iff (ndim-1) ln zz + lp' - lp > ln u.  The logarithms were taken in FP32
-          // (|error| < 1e-5): unless the margin is below the threshold the FP64 decision is already
-          // determined; otherwise (about 1 proposal in 10^4) it is recomputed in FP64 as the oracle does.
-          const double est = __dsub_rn(lpn, lpo) + f32_widen_int(lfb[q]);
-          bool accept;
-          if (!accept_filter(est, lpn, lpo, accept)) {
-            const u32x4 r = philox4x32_10((uint32_t)q, t, spec, (uint32_t)(1 + sp), k0, k1);     // re-draw u2
-            const double lnpdiff = __dsub_rn(__dadd_rn(__dmul_rn((double)(ndim - 1), log(zzb[q])), lpn), lpo);
-            accept = lnpdiff > log(u53_int(r.w, (r.z << 16) | 0x8000u));
-          }
-          if (accept) {
-            copy_dims(s.coords + k * ndim, s.prop + q * ndim, ndim);
-            s.lp[k] = lpn;
-            s.acc[k] += 1;
-          }
+      // ---- ACCEPT (threads [0,Hs)) while the other threads draw the random numbers of the next half-step (measured:
+      //      running the draws as side work under the evaluation instead is 5-8 % slower for every evaluator — they
+      //      land on the evaluation's critical path, here they are off it); then the shuffle keys of the next step
+      //      (first half-step) or the scan + placement of its key ranking (second half-step) ---------------------------
+      {
+        const int nspare = NT - min(Hs, NT);
+        const bool spare = tid >= Hs;
+        if (spare || nspare == 0)
+          draw_rows(dctx, sp == 0 ? t : t + 1u, sp ^ 1, spare ? tid - Hs : tid, spare ? nspare : NT);
+      }
+      for (int q = tid; q < Hs; q += NT) {
+        const int k = list[off + q];
+        const double lpo = s.lp[k];
+        const double lpn = s.inb[q] ? -0.5 * (ev.chi_of(s.chi, q) + llc) : neg_inf();
+        if (lpn != lpn) flag |= 1;
+        // emcee: accept iff (ndim-1) ln zz + lp' - lp > ln u.  The logarithms were taken in FP32
+        // (|error| < 1e-5): unless the margin is below the threshold the FP64 decision is already
+        // determined; otherwise (about 1 proposal in 10^4) it is recomputed in FP64 as the oracle does.
+        const double est = __dsub_rn(lpn, lpo) + f32_widen_int(lfb[q]);
+        bool accept;
+        if (!accept_filter(est, lpn, lpo, accept)) {
+          const u32x4 r = philox4x32_10((uint32_t)q, t, spec, (uint32_t)(1 + sp), k0, k1);     // re-draw u2
+          const double lnpdiff = __dsub_rn(__dadd_rn(__dmul_rn((double)(ndim - 1), log(zzb[q])), lpn), lpo);
+          accept = lnpdiff > log(u53_int(r.w, (r.z << 16) | 0x8000u));
+        }
+        if (accept) {
+          copy_dims(s.coords + k * ndim, s.prop + q * ndim, ndim);
+          s.lp[k] = lpn;
+          s.acc[k] += 1;
         }
       }
       FINE_MARK(10)
-      {
-        // spare threads (those beyond the Hs acceptors) prepare the next half-step
-        const int nspare = NT - min(Hs, NT);
-        const bool spare = tid >= Hs;
-        const int worker = spare ? tid - Hs : tid, nworkers = spare ? nspare : NT;
-        if (spare || nspare == 0)
-          gen_proposal_draws(sp == 0 ? t : t + 1u, sp ^ 1, worker, nworkers);
-        if (sp == 0 && (!spare || Hs >= NT)) gen_keys(t + 1u, tid, min(Hs, NT));
-      }
+      if (sp == 0) gen_keys(t + 1u, tid, NT);
       FINE_MARK(11)
       __syncthreads();
       PHASE_MARK(3)
     }
-    // ---- split of the next step: rank its keys (drawn during this step's first accept phase) ---------
-    if (W <= NT) {
+    // ---- split of the next step: rank its keys (drawn during this step's first accept phase).  (Spreading the binned
+    //      ranking over the barriers of the second half-step, as the warp-private kernel does, measured 2-3 % slower
+    //      here: the per-warp scan lands on the accept phase of all eight warps.) ------------------------------------
+    if (binned) {
       rank_keys_binned<NT>(s.keys, list_next, W, s.hist, s.sorted);
     } else {
       side.begin(s.keys, list_next, W, 0);
       side.finish();
     }
     PHASE_MARK(0)
+    // (the proposals of the next step read list_next and coords: synchronise here)
+    __syncthreads();
     // ---- backend.save_step: chain[it] = coords ; log_prob[it] = lp -----------------------------
     // (no barrier needed in between: the next reader of list_next / coords is behind the barrier
     //  that ends the next PROPOSE phase... the proposals read list_next, so synchronise here)
