@@ -379,31 +379,32 @@ __device__ __forceinline__ void rank_keys_binned(const uint32_t* __restrict__ ke
   }
 }
 
-// Binned key ranking (rank_keys_binned of sampler.cuh) cut at its barriers so that the sampler can place the pieces
-// between the barriers it has anyway.  `hist` must be zero on entry of part A.
-//   A  slot of every key inside its bin                       (needs: keys visible)          -> returns (key, bin, slot)
+// Binned key ranking (rank_keys_binned above) cut at its barriers so that the warp-private sampler can place the pieces
+// between the barriers it has anyway.  `counts` must be zero on entry of part A and is left intact by B and C.
+//   A  slot of every key inside its bin                       (needs: keys visible)          -> (key, bin, slot)
 //   -- barrier --
-//   B  every warp scans the 256 bin counts itself and writes the SAME starts (benign identical stores), then places
-//      its keys:  sorted[start + slot] = key
+//   B  every warp scans the 256 bin counts itself (8 per lane + a shuffle scan) and hands each of its threads the start of
+//      its bin by shuffle — no shared array of starts, nothing written but sorted[start + slot] = key
 //   -- barrier --
 //   C  rank = start + smaller keys in the own bin ; list_out[rank] = walker
 template <int NT>
-__device__ __forceinline__ void rank_part_a(const uint32_t* __restrict__ keys, int W, int* __restrict__ hist,
+__device__ __forceinline__ void rank_part_a(const uint32_t* __restrict__ keys, int W, int* __restrict__ counts,
                                             uint32_t& key, int& bin, int& slot) {
   const int tid = threadIdx.x;
   key = 0; bin = 0; slot = 0;
   if (tid < W) {
     key = keys[tid];
     bin = (int)(key >> 24);
-    slot = atomicAdd(&hist[bin], 1);
+    slot = atomicAdd(&counts[bin], 1);
   }
 }
 template <int NT>
-__device__ __forceinline__ int rank_part_b(int W, int* __restrict__ hist, int* __restrict__ starts, uint32_t* __restrict__ sorted,
+__device__ __forceinline__ int rank_part_b(int W, const int* __restrict__ counts, uint32_t* __restrict__ sorted,
                                            uint32_t key, int bin, int slot) {
   const int tid = threadIdx.x, lane = tid & 31;
-  {                                                // exclusive scan of the 256 counters, 8 per lane, by every warp
-    const int4* h4 = reinterpret_cast<const int4*>(hist);
+  int pre[8];                                      // exclusive prefix of bins 8 lane ... 8 lane + 7
+  {
+    const int4* h4 = reinterpret_cast<const int4*>(counts);
     const int4 a = h4[2 * lane], c = h4[2 * lane + 1];
     const int s0 = a.x, s1 = s0 + a.y, s2 = s1 + a.z, s3 = s2 + a.w, s4 = s3 + c.x, s5 = s4 + c.y, s6 = s5 + c.z;
     const int tot = s6 + c.w;
@@ -414,25 +415,24 @@ __device__ __forceinline__ int rank_part_b(int W, int* __restrict__ hist, int* _
       if (lane >= o) inc += n;
     }
     const int base = inc - tot;
-    int4* o4 = reinterpret_cast<int4*>(starts);
-    o4[2 * lane] = make_int4(base, base + s0, base + s1, base + s2);
-    o4[2 * lane + 1] = make_int4(base + s3, base + s4, base + s5, base + s6);
-    if (lane == 31) starts[256] = inc;
+    pre[0] = base; pre[1] = base + s0; pre[2] = base + s1; pre[3] = base + s2;
+    pre[4] = base + s3; pre[5] = base + s4; pre[6] = base + s5; pre[7] = base + s6;
   }
-  __syncwarp();
   int start = 0;
-  if (tid < W) {
-    start = starts[bin];
-    sorted[start + slot] = key;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int v = __shfl_sync(0xffffffffu, pre[e], bin >> 3);
+    if ((bin & 7) == e) start = v;
   }
+  if (tid < W) sorted[start + slot] = key;
   return start;
 }
 template <int NT>
-__device__ __forceinline__ void rank_part_c(int W, const int* __restrict__ starts, const uint32_t* __restrict__ sorted,
+__device__ __forceinline__ void rank_part_c(int W, const int* __restrict__ counts, const uint32_t* __restrict__ sorted,
                                             int* __restrict__ list_out, uint32_t key, int bin, int start) {
   const int tid = threadIdx.x;
   if (tid < W) {
-    const int end = starts[bin + 1];
+    const int end = start + counts[bin];
     int cnt = 0;
     for (int j = start; j < end; ++j) cnt += sorted[j] < key ? 1 : 0;
     list_out[start + cnt] = tid;

@@ -15,7 +15,8 @@
 //              draw the next step's shuffle keys
 // The draws and the accept threshold are assembled on the integer / FP32 pipes (u53_int, f32_widen_int): in these phases
 // every FP64-pipe instruction queues behind the other warps' tensor tiles.  The key ranking of the next split takes two
-// barriers per step (every warp scans the 256-bin histogram itself), so a step has four CTA barriers instead of eleven.
+// barriers per step (every warp scans the 256-bin histogram itself and hands the bin starts to its threads by shuffle),
+// so a step has four CTA barriers instead of eleven.
 // CTA = 32 * ceil(W / 32) threads rounded up to a power of two (32 ... 256): every warp owns one row tile per half-step,
 // a 32-walker ensemble is a single-warp CTA.  W <= 256; larger ensembles, clustered and tcgen05 evaluators use
 // ensemble_kernel (sampler.cuh).
@@ -37,7 +38,7 @@ struct WpSmem {
   int* list;        // [2][W]            walker at rank, by step parity
   int* acc;         // [W]
   int* partner;     // [2][2][rows_pad]
-  int* hist;        // [2][260]          key ranking: bucket counters | scanned bucket starts
+  int* hist;        // [260]             key ranking: bucket counters (zero between rankings)
   uint32_t* sorted; // [Wpad4]
 };
 
@@ -46,7 +47,7 @@ __host__ __device__ inline int wp_rows_pad(int W) { return ceil_div((W + 1) / 2,
 __host__ __device__ inline size_t wp_smem_bytes(int W, int ndim) {
   const int rp = wp_rows_pad(W);
   const size_t dbl = (size_t)W * ndim + W + (size_t)rp * ndim + 4 * (size_t)rp + 8 + 4 * (size_t)ndim;
-  const size_t words = 4 * (size_t)rp + (size_t)(W + 4) + 2 * W + W + 4 * rp + 2 * 260 + (W + 4);
+  const size_t words = 4 * (size_t)rp + (size_t)(W + 4) + 2 * W + W + 4 * rp + 260 + (W + 4);
   return dbl * 8 + words * 4 + 64;
 }
 
@@ -65,7 +66,7 @@ __device__ inline void wp_carve(WpSmem& s, double* base, int W, int ndim) {
   s.acc = s.list + 2 * W;
   s.partner = s.acc + W;
   s.hist = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(s.partner + 4 * rp) + 15) & ~uintptr_t(15));
-  s.sorted = reinterpret_cast<uint32_t*>(s.hist + 2 * 260);
+  s.sorted = reinterpret_cast<uint32_t*>(s.hist + 260);
 }
 
 // ---- evaluators -------------------------------------------------------------------------------------------------------
@@ -397,7 +398,6 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_wp_kernel(const EnsemblePar
   double* p = wp_eval_carve(ev, smem, rows_pad);
   wp_carve(s, p, W, ndim);
   int* const counts = s.hist;                        // bin counters of the key ranking (zero between rankings)
-  int* const starts = s.hist + 260;                  // scanned bin starts (every warp writes the same values)
 
   // ---- per-spectrum constants + initial ensemble ---------------------------------------
   for (int i = tid; i < 2 * ndim; i += NT) {
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_wp_kernel(const EnsemblePar
   for (int i = tid; i < W * ndim; i += NT) s.coords[i] = gc[i];
   for (int i = tid; i < W; i += NT) s.acc[i] = 0;
   for (int i = tid; i < rows_pad * ndim; i += NT) s.prop[i] = 0.0;
-  for (int i = tid; i < 2 * 260; i += NT) s.hist[i] = 0;
+  for (int i = tid; i < 260; i += NT) s.hist[i] = 0;
   ev.init(P.d, P.w + (size_t)b * P.w_stride, P.taus + (size_t)b * P.tau_stride,
           P.log_taus + (size_t)b * P.tau_stride * P.d.n_coef, P.y + (size_t)b * 2 * P.d.n_freq,
           P.yerr + (size_t)b * 2 * P.d.n_freq, s.red);   // ends with __syncthreads()
@@ -490,9 +490,9 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_wp_kernel(const EnsemblePar
     uint32_t key; int bin, slot;
     rank_part_a<NT>(s.keys, W, counts, key, bin, slot);
     __syncthreads();
-    const int start = rank_part_b<NT>(W, counts, starts, s.sorted, key, bin, slot);
+    const int start = rank_part_b<NT>(W, counts, s.sorted, key, bin, slot);
     __syncthreads();
-    rank_part_c<NT>(W, starts, s.sorted, s.list + (size_t)(P.step0 & 1) * W, key, bin, start);
+    rank_part_c<NT>(W, counts, s.sorted, s.list + (size_t)(P.step0 & 1) * W, key, bin, start);
     __syncthreads();
     for (int i = tid; i < 260; i += NT) counts[i] = 0;
   }
@@ -570,9 +570,9 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_wp_kernel(const EnsemblePar
       ++kept;
     }
     // ---- split of the next step (its bin counts were taken during the second half-step) -----------------------
-    const int rk_start = rank_part_b<NT>(W, counts, starts, s.sorted, rk_key, rk_bin, rk_slot);
+    const int rk_start = rank_part_b<NT>(W, counts, s.sorted, rk_key, rk_bin, rk_slot);
     __syncthreads();
-    rank_part_c<NT>(W, starts, s.sorted, list_next, rk_key, rk_bin, rk_start);
+    rank_part_c<NT>(W, counts, s.sorted, list_next, rk_key, rk_bin, rk_start);
     __syncthreads();
     for (int i = tid; i < 260; i += NT) counts[i] = 0;        // next incremented behind the next step's first barrier
   }
