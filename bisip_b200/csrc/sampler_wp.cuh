@@ -25,6 +25,20 @@
 
 namespace bisip {
 
+// Developer build (-DBISIP_PHASE_TIMING, `make dbg`): lane 0 of warp 0 of block 0 accumulates SM cycles per section of a
+// half-step and prints them at the end.  Compiled out of the product library.
+#ifdef BISIP_PHASE_TIMING
+#define WP_T_DECL long long wt_[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long wt0_ = clock64();
+#define WP_T(i) { long long n_ = clock64(); wt_[i] += n_ - wt0_; wt0_ = n_; }
+#define WP_T_PRINT if (blockIdx.x == 0 && threadIdx.x == 0) printf("wp cycles/step (warp 0): propose %.0f  prepare+sync %.0f  eval %.0f  accept %.0f  draws+keys/rankA %.0f  barrier-wait %.0f  store %.0f  rankB %.0f  barrier %.0f  rankC+barrier+zero %.0f\n", \
+    (double)wt_[0] / P.nsteps, (double)wt_[1] / P.nsteps, (double)wt_[2] / P.nsteps, (double)wt_[3] / P.nsteps, (double)wt_[4] / P.nsteps, \
+    (double)wt_[5] / P.nsteps, (double)wt_[6] / P.nsteps, (double)wt_[7] / P.nsteps, (double)wt_[8] / P.nsteps, (double)wt_[9] / P.nsteps);
+#else
+#define WP_T_DECL
+#define WP_T(i)
+#define WP_T_PRINT
+#endif
+
 struct WpSmem {
   double* coords;   // [W][ndim]
   double* lp;       // [W]
@@ -499,6 +513,7 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_wp_kernel(const EnsemblePar
   gen_draws((uint32_t)P.step0);
   __syncthreads();
 
+  WP_T_DECL
   for (int it = 0; it < P.nsteps; ++it) {
     const uint32_t t = (uint32_t)(P.step0 + it);
     const int par = (int)(t & 1u);
@@ -522,12 +537,15 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_wp_kernel(const EnsemblePar
         }
         const unsigned okm = __ballot_sync(0xffffffffu, ok);
         inb = ((okm >> (lane & ~1)) & 3u) == 3u;
+        WP_T(0)
         if (Eval::kNeedsPrepare) {
           __syncwarp();
           if (sub == 0 && q < Hs) ev.prepare_row(q, s.prop + q * ndim);
         }
         __syncwarp();
+        WP_T(1)
         const double chi = ev.eval_warp(s.prop, ndim, row0, Hs, lane);
+        WP_T(2)
         if (sub == 0 && q < Hs) {
           const double lpo = s.lp[k];
           const double lpn = inb ? -0.5 * (chi + llc) : neg_inf();
@@ -547,6 +565,7 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_wp_kernel(const EnsemblePar
           }
         }
       }
+      WP_T(3)
       if (sp == 0) {
         // the random numbers of the NEXT step: its draws (every lane), its shuffle keys (the first Wpad4/4 threads)
         gen_draws(t + 1u);
@@ -554,7 +573,9 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_wp_kernel(const EnsemblePar
       } else {
         rank_part_a<NT>(s.keys, W, counts, rk_key, rk_bin, rk_slot);         // keys: visible since the sp = 0 barrier
       }
+      WP_T(4)
       __syncthreads();
+      WP_T(5)
     }
     // ---- backend.save_step: chain[it] = coords ; log_prob[it] = lp.  Before the ranking barriers: they separate these
     //      reads of coords from the next half-step's accepts (a warp no longer waits for the others in between) -------
@@ -569,13 +590,18 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_wp_kernel(const EnsemblePar
       }
       ++kept;
     }
+    WP_T(6)
     // ---- split of the next step (its bin counts were taken during the second half-step) -----------------------
     const int rk_start = rank_part_b<NT>(W, counts, s.sorted, rk_key, rk_bin, rk_slot);
+    WP_T(7)
     __syncthreads();
+    WP_T(8)
     rank_part_c<NT>(W, counts, s.sorted, list_next, rk_key, rk_bin, rk_start);
     __syncthreads();
     for (int i = tid; i < 260; i += NT) counts[i] = 0;        // next incremented behind the next step's first barrier
+    WP_T(9)
   }
+  WP_T_PRINT
   // ---- final state ------------------------------------------------------------------------------
   double* gco = P.coords + (size_t)b * W * ndim;
   for (int i = tid; i < W * ndim; i += NT) gco[i] = s.coords[i];
