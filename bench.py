@@ -201,11 +201,11 @@ def dmma_peak():
 
 
 def kernel_sources_sha():
-    """Hash of the sources that define the dominant kernel (ensemble_kernel<DecompEvaluator>): the committed ncu DRAM
-    figure is only quoted while they are unchanged."""
+    """Hash of the sources that define the dominant kernel (ensemble_wp_kernel<DecompMmaWarpEvaluator>): the committed ncu
+    DRAM figure is only quoted while they are unchanged."""
     import hashlib
     h = hashlib.sha256()
-    for f in ("sampler.cuh", "decomp_eval.cuh", "common.cuh"):
+    for f in ("sampler_wp.cuh", "sampler.cuh", "decomp_eval.cuh", "common.cuh"):
         with open(os.path.join(ROOT, "bisip_b200", "csrc", f), "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()[:16]
@@ -607,7 +607,7 @@ def run_gpu(args):
                     "api": "bisip_b200.BatchInversion.fit_gathered (pinned host zn/zn_err/p0 of the shard in; for N>1 the NCCL "
                            "gather of the summaries is inside the timed region; the complete host result on every rank)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "ensemble_kernel<DecompEvaluator<4>> (bisip_ensemble_run)",
+            "roofline": {"bound": "tensor", "kernel": "ensemble_wp_kernel<DecompMmaWarpEvaluator<4>, 2, 256> (bisip_ensemble_run)",
                          "achieved": achieved, "peak": peak_sust, "unit": "TFLOP/s", "frac": achieved / peak_sust,
                          "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes": float(B) * (nk * WALKERS * inv.ndim * 8 + 2 * WALKERS * inv.ndim * 8

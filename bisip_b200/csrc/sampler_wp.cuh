@@ -529,12 +529,13 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_wp_kernel(const EnsemblePar
       int k = 0;
       if (row0 < Hs) {
         // ---- this warp's 16 rows: propose | evaluate | accept, no CTA barrier in between ---------------------
-        bool ok = true;
-        if (q < Hs) {
-          const int j = list[coff + s.partner[dq]];
-          k = list[off + q];
-          ok = propose_pair(s.coords + j * ndim, s.coords + k * ndim, s.zz[dq], s.prop + q * ndim, s.bkey, ndim, sub);
-        }
+        // rows beyond the half-step (only in its last, partly filled tile) rebuild this warp's first row into their own
+        // padding row: no divergent region around the proposal, and no read of a walker another warp may be updating
+        const int qe = q < Hs ? q : row0;
+        const int dqe = dq - q + qe;
+        const int j = list[coff + s.partner[dqe]];
+        k = list[off + qe];
+        const bool ok = propose_pair(s.coords + j * ndim, s.coords + k * ndim, s.zz[dqe], s.prop + q * ndim, s.bkey, ndim, sub);
         const unsigned okm = __ballot_sync(0xffffffffu, ok);
         inb = ((okm >> (lane & ~1)) & 3u) == 3u;
         WP_T(0)
@@ -546,7 +547,7 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_wp_kernel(const EnsemblePar
         WP_T(1)
         const double chi = ev.eval_warp(s.prop, ndim, row0, Hs, lane);
         WP_T(2)
-        if (sub == 0 && q < Hs) {
+        if (q < Hs) {                  // both lanes of the row take the (identical) decision: no divergence on `sub`
           const double lpo = s.lp[k];
           const double lpn = inb ? -0.5 * (chi + llc) : neg_inf();
           if (lpn != lpn) flag |= 1;
@@ -558,7 +559,7 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_wp_kernel(const EnsemblePar
             const double lnpdiff = __dsub_rn(__dadd_rn(__dmul_rn((double)(ndim - 1), log(s.zz[dq])), lpn), lpo);
             accept = lnpdiff > log(u53_int(rr.w, (rr.z << 16) | 0x8000u));
           }
-          if (accept) {
+          if (accept && sub == 0) {
             copy_dims(s.coords + k * ndim, s.prop + q * ndim, ndim);
             s.lp[k] = lpn;
             s.acc[k] += 1;
