@@ -29,6 +29,10 @@ def test_fit_sharded_single_process_equals_batch_fit():
     for k in ('percentiles', 'mean', 'std', 'acceptance_fraction', 'flags', 'chain'):
         np.testing.assert_array_equal(res[k], ref[k])
     assert res['shard'] == (0, 12)
+    inv = bb.BatchInversion('dias', syn['w'], syn['zn'], syn['zn_err'], **kw)
+    got = inv.fit_gathered(12, discard=40, thin=2)                  # no process group: equals fit()
+    for k in ('percentiles', 'mean', 'std', 'acceptance_fraction', 'flags'):
+        np.testing.assert_array_equal(got[k], ref[k])
 
 
 _NCCL_WORKER = r'''
