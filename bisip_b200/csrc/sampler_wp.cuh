@@ -14,9 +14,10 @@
 //              uniform of row r of half-step `sub` of the NEXT step (all lanes busy, no divergence); warps 0-1 also
 //              draw the next step's shuffle keys
 // The draws and the accept threshold are assembled on the integer / FP32 pipes (u53_int, f32_widen_int): in these phases
-// every FP64-pipe instruction queues behind the other warps' tensor tiles.  The key ranking of the next split takes two
-// barriers per step (every warp scans the 256-bin histogram itself and hands the bin starts to its threads by shuffle),
-// so a step has four CTA barriers instead of eleven.
+// every FP64-pipe instruction queues behind the other warps' tensor tiles.  The key ranking of the next split is cut into
+// three parts (every warp scans the 256-bin histogram itself and hands the bin starts to its threads by shuffle) that run
+// one step ahead, between the two half-step barriers: a step has TWO CTA barriers (three when it is stored) instead of
+// eleven.
 // CTA = 32 * ceil(W / 32) threads rounded up to a power of two (32 ... 256): every warp owns one row tile per half-step,
 // a 32-walker ensemble is a single-warp CTA.  W <= 256; larger ensembles, clustered and tcgen05 evaluators use
 // ensemble_kernel (sampler.cuh).
@@ -30,9 +31,9 @@ namespace bisip {
 #ifdef BISIP_PHASE_TIMING
 #define WP_T_DECL long long wt_[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long wt0_ = clock64();
 #define WP_T(i) { long long n_ = clock64(); wt_[i] += n_ - wt0_; wt0_ = n_; }
-#define WP_T_PRINT if (blockIdx.x == 0 && threadIdx.x == 0) printf("wp cycles/step (warp 0): propose %.0f  prepare+sync %.0f  eval %.0f  accept %.0f  draws+keys/rankA %.0f  barrier-wait %.0f  store %.0f  rankB %.0f  barrier %.0f  rankC+barrier+zero %.0f\n", \
+#define WP_T_PRINT if (blockIdx.x == 0 && threadIdx.x == 0) printf("wp cycles/step (warp 0): propose %.0f  prepare+sync %.0f  eval %.0f  accept %.0f  draws+keys+ranking %.0f  barrier-wait %.0f  store %.0f\n", \
     (double)wt_[0] / P.nsteps, (double)wt_[1] / P.nsteps, (double)wt_[2] / P.nsteps, (double)wt_[3] / P.nsteps, (double)wt_[4] / P.nsteps, \
-    (double)wt_[5] / P.nsteps, (double)wt_[6] / P.nsteps, (double)wt_[7] / P.nsteps, (double)wt_[8] / P.nsteps, (double)wt_[9] / P.nsteps);
+    (double)wt_[5] / P.nsteps, (double)wt_[6] / P.nsteps);
 #else
 #define WP_T_DECL
 #define WP_T(i)
@@ -52,7 +53,7 @@ struct WpSmem {
   int* list;        // [2][W]            walker at rank, by step parity
   int* acc;         // [W]
   int* partner;     // [2][2][rows_pad]
-  int* hist;        // [260]             key ranking: bucket counters (zero between rankings)
+  int* hist;        // [2][260]          key ranking: bucket counters, by parity of the step the keys belong to
   uint32_t* sorted; // [Wpad4]
 };
 
@@ -61,7 +62,7 @@ __host__ __device__ inline int wp_rows_pad(int W) { return ceil_div((W + 1) / 2,
 __host__ __device__ inline size_t wp_smem_bytes(int W, int ndim) {
   const int rp = wp_rows_pad(W);
   const size_t dbl = (size_t)W * ndim + W + (size_t)rp * ndim + 4 * (size_t)rp + 8 + 4 * (size_t)ndim;
-  const size_t words = 4 * (size_t)rp + (size_t)(W + 4) + 2 * W + W + 4 * rp + 260 + (W + 4);
+  const size_t words = 4 * (size_t)rp + (size_t)(W + 4) + 2 * W + W + 4 * rp + 2 * 260 + (W + 4);
   return dbl * 8 + words * 4 + 64;
 }
 
@@ -80,7 +81,7 @@ __device__ inline void wp_carve(WpSmem& s, double* base, int W, int ndim) {
   s.acc = s.list + 2 * W;
   s.partner = s.acc + W;
   s.hist = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(s.partner + 4 * rp) + 15) & ~uintptr_t(15));
-  s.sorted = reinterpret_cast<uint32_t*>(s.hist + 260);
+  s.sorted = reinterpret_cast<uint32_t*>(s.hist + 2 * 260);
 }
 
 // ---- evaluators -------------------------------------------------------------------------------------------------------
@@ -407,11 +408,13 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_wp_kernel(const EnsemblePar
   const int r = lane >> 1, sub = lane & 1;
   const int row0 = 16 * warp, q = row0 + r;         // this lane's proposal row in every half-step
 
+  // (a start-time stagger of the two co-resident CTAs of the DMMA kernel, as ensemble_kernel has, changes nothing here:
+  //  1.750e9 +- 0.1 % for 0 ... 20 us)
   Eval ev(P.d);
   WpSmem s;
   double* p = wp_eval_carve(ev, smem, rows_pad);
   wp_carve(s, p, W, ndim);
-  int* const counts = s.hist;                        // bin counters of the key ranking (zero between rankings)
+  int* const counts = s.hist;                        // [2][260] bin counters of the key ranking
 
   // ---- per-spectrum constants + initial ensemble ---------------------------------------
   for (int i = tid; i < 2 * ndim; i += NT) {
@@ -422,7 +425,7 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_wp_kernel(const EnsemblePar
   for (int i = tid; i < W * ndim; i += NT) s.coords[i] = gc[i];
   for (int i = tid; i < W; i += NT) s.acc[i] = 0;
   for (int i = tid; i < rows_pad * ndim; i += NT) s.prop[i] = 0.0;
-  for (int i = tid; i < 260; i += NT) s.hist[i] = 0;
+  for (int i = tid; i < 2 * 260; i += NT) s.hist[i] = 0;
   ev.init(P.d, P.w + (size_t)b * P.w_stride, P.taus + (size_t)b * P.tau_stride,
           P.log_taus + (size_t)b * P.tau_stride * P.d.n_coef, P.y + (size_t)b * 2 * P.d.n_freq,
           P.yerr + (size_t)b * 2 * P.d.n_freq, s.red);   // ends with __syncthreads()
@@ -497,20 +500,30 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_wp_kernel(const EnsemblePar
     s.lf[o] = nd1f * __logf(zzf) - __logf(u2f);
   };
 
-  // prologue: split of step 0 and the draws of both its half-steps
-  for (int c = tid; c < Wpad4 / 4; c += NT) gen_keys_chunk((uint32_t)P.step0, c);
+  // The split of step t+1 is ranked one step AHEAD of its use, its three parts riding on the two barriers a step has anyway:
+  //   step t-1, second half-step   part A of keys(t+1)  (bin slots; the keys were drawn in that step's first half-step)
+  //   step t,   first half-step    part B               (scan + placement)
+  //   step t,   second half-step   part C               (rank -> list of step t+1), then part A of keys(t+2)
+  // counts[c] serves the keys of steps with parity c; it is zeroed in the first half-step of the step after its last use.
+  // prologue: the split of step 0 in full, parts A of keys(step0 + 1), and the draws of both half-steps of step 0
+  const uint32_t t0 = (uint32_t)P.step0;
+  uint32_t rk_key = 0;
+  int rk_bin = 0, rk_slot = 0, rk_start = 0;
+  for (int c = tid; c < Wpad4 / 4; c += NT) gen_keys_chunk(t0, c);
   __syncthreads();
   {
-    uint32_t key; int bin, slot;
-    rank_part_a<NT>(s.keys, W, counts, key, bin, slot);
+    int* cnt0 = counts + (t0 & 1u) * 260;
+    rank_part_a<NT>(s.keys, W, cnt0, rk_key, rk_bin, rk_slot);
     __syncthreads();
-    const int start = rank_part_b<NT>(W, counts, s.sorted, key, bin, slot);
+    rk_start = rank_part_b<NT>(W, cnt0, s.sorted, rk_key, rk_bin, rk_slot);
     __syncthreads();
-    rank_part_c<NT>(W, counts, s.sorted, s.list + (size_t)(P.step0 & 1) * W, key, bin, start);
+    rank_part_c<NT>(W, cnt0, s.sorted, s.list + (size_t)(t0 & 1u) * W, rk_key, rk_bin, rk_start);
+    for (int c = tid; c < Wpad4 / 4; c += NT) gen_keys_chunk(t0 + 1u, c);       // keys[] was last read in part A above
     __syncthreads();
-    for (int i = tid; i < 260; i += NT) counts[i] = 0;
+    for (int i = tid; i < 260; i += NT) cnt0[i] = 0;
+    rank_part_a<NT>(s.keys, W, counts + ((t0 + 1u) & 1u) * 260, rk_key, rk_bin, rk_slot);
   }
-  gen_draws((uint32_t)P.step0);
+  gen_draws(t0);
   __syncthreads();
 
   WP_T_DECL
@@ -519,8 +532,8 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_wp_kernel(const EnsemblePar
     const int par = (int)(t & 1u);
     const int* list = s.list + (size_t)par * W;               // this step's split
     int* list_next = s.list + (size_t)(par ^ 1) * W;
-    uint32_t rk_key = 0;
-    int rk_bin = 0, rk_slot = 0;
+    int* cnt_next = counts + (par ^ 1) * 260;                 // bin counts of keys(t+1) (part A ran one half-step ago)
+    int* cnt_after = counts + par * 260;                      // will count keys(t+2)
     for (int sp = 0; sp < 2; ++sp) {
       const int off = sp ? H0 : 0, Hs = sp ? W - H0 : H0;
       const int coff = sp ? 0 : H0;
@@ -547,7 +560,7 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_wp_kernel(const EnsemblePar
         WP_T(1)
         const double chi = ev.eval_warp(s.prop, ndim, row0, Hs, lane);
         WP_T(2)
-        if (q < Hs) {                  // both lanes of the row take the (identical) decision: no divergence on `sub`
+        if (sub == 0 && q < Hs) {
           const double lpo = s.lp[k];
           const double lpn = inb ? -0.5 * (chi + llc) : neg_inf();
           if (lpn != lpn) flag |= 1;
@@ -559,7 +572,7 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_wp_kernel(const EnsemblePar
             const double lnpdiff = __dsub_rn(__dadd_rn(__dmul_rn((double)(ndim - 1), log(s.zz[dq])), lpn), lpo);
             accept = lnpdiff > log(u53_int(rr.w, (rr.z << 16) | 0x8000u));
           }
-          if (accept && sub == 0) {
+          if (accept) {
             copy_dims(s.coords + k * ndim, s.prop + q * ndim, ndim);
             s.lp[k] = lpn;
             s.acc[k] += 1;
@@ -568,18 +581,22 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_wp_kernel(const EnsemblePar
       }
       WP_T(3)
       if (sp == 0) {
-        // the random numbers of the NEXT step: its draws (every lane), its shuffle keys (the first Wpad4/4 threads)
+        // the random numbers of the NEXT step (every lane); the shuffle keys of the step after it (the first Wpad4/4
+        // threads; keys[] was last read one half-step ago); scan + placement of the next step's ranking
         gen_draws(t + 1u);
-        if (tid < Wpad4 / 4) gen_keys_chunk(t + 1u, tid);
+        if (tid < Wpad4 / 4) gen_keys_chunk(t + 2u, tid);
+        rk_start = rank_part_b<NT>(W, cnt_next, s.sorted, rk_key, rk_bin, rk_slot);
+        for (int i = tid; i < 260; i += NT) cnt_after[i] = 0;
       } else {
-        rank_part_a<NT>(s.keys, W, counts, rk_key, rk_bin, rk_slot);         // keys: visible since the sp = 0 barrier
+        rank_part_c<NT>(W, cnt_next, s.sorted, list_next, rk_key, rk_bin, rk_start);      // the split of step t+1
+        rank_part_a<NT>(s.keys, W, cnt_after, rk_key, rk_bin, rk_slot);                   // keys(t+2): bin slots
       }
       WP_T(4)
       __syncthreads();
       WP_T(5)
     }
-    // ---- backend.save_step: chain[it] = coords ; log_prob[it] = lp.  Before the ranking barriers: they separate these
-    //      reads of coords from the next half-step's accepts (a warp no longer waits for the others in between) -------
+    // ---- backend.save_step: chain[it] = coords ; log_prob[it] = lp; the barrier separates these reads of coords from the
+    //      next half-step's accepts (a warp does not wait for the others between its proposal and its accept any more) --
     if (it >= first && (it - first) % P.thin == 0) {
       if (P.chain != nullptr) {
         double* dst = P.chain + ((size_t)b * P.nkeep + kept) * W * ndim;
@@ -590,17 +607,9 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_wp_kernel(const EnsemblePar
         for (int i = tid; i < W; i += NT) __stcs(dst + i, s.lp[i]);
       }
       ++kept;
+      __syncthreads();
     }
     WP_T(6)
-    // ---- split of the next step (its bin counts were taken during the second half-step) -----------------------
-    const int rk_start = rank_part_b<NT>(W, counts, s.sorted, rk_key, rk_bin, rk_slot);
-    WP_T(7)
-    __syncthreads();
-    WP_T(8)
-    rank_part_c<NT>(W, counts, s.sorted, list_next, rk_key, rk_bin, rk_start);
-    __syncthreads();
-    for (int i = tid; i < 260; i += NT) counts[i] = 0;        // next incremented behind the next step's first barrier
-    WP_T(9)
   }
   WP_T_PRINT
   // ---- final state ------------------------------------------------------------------------------
