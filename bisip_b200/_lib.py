@@ -23,7 +23,7 @@ ABI_VERSION = 2
 EXPORTS = ("bisip_abi_version", "bisip_last_error", "bisip_launch_count", "bisip_forward",
            "bisip_log_probability", "bisip_decomp_build_kernel", "bisip_n_keep",
            "bisip_ensemble_run", "bisip_column_stats_workspace", "bisip_column_stats",
-           "bisip_decomp_kernel_kind", "bisip_model_percentile")
+           "bisip_decomp_kernel_kind", "bisip_model_percentile", "bisip_gauss_loglike")
 KERNEL_KINDS = {0: "dmma", 1: "dmma-cluster", 2: "mma-tf32", 3: "tcgen05", 4: "tcgen05-cluster", 5: "fp64-collapsed"}
 
 
@@ -63,6 +63,8 @@ def load():
                                           vp, vp, vp, vp, vp]
     lib.bisip_decomp_build_kernel.restype = C.c_int
     lib.bisip_decomp_build_kernel.argtypes = [vp, i32, vp, i32, dbl, vp, vp]
+    lib.bisip_gauss_loglike.restype = C.c_int
+    lib.bisip_gauss_loglike.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     lib.bisip_ensemble_run.restype = C.c_int
     lib.bisip_ensemble_run.argtypes = [C.POINTER(ModelDesc), i32, i32, i32, i32, C.c_uint64, C.c_uint32,
                                        dbl, i32, i32, vp, i64, vp, vp, i64, vp, vp, vp,

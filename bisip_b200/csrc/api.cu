@@ -91,6 +91,23 @@ __global__ void build_kernel_matrix(const double* w, int N, const double* taus, 
   }
 }
 
+// Gaussian log-likelihood of n model rows Z[n][2N] supplied by the caller (a user forward callable evaluated on the host,
+// models.py:59-62): one warp per row, lanes stride the 2N columns, fixed-order shuffle reduction.
+__global__ void gauss_loglike_kernel(const double* __restrict__ Z, const double* __restrict__ y,
+                                     const double* __restrict__ yerr, int C, int n, double* __restrict__ out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const double* z = Z + (size_t)row * C;
+  double acc = 0.0;
+  for (int c = lane; c < C; c += 32) {
+    const double e = yerr[c], s2 = e * e, r = y[c] - z[c];
+    acc += r * r / s2 + 2.0 * log(s2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[row] = -0.5 * acc;
+}
+
 }  // namespace
 
 extern "C" {
@@ -153,6 +170,16 @@ int bisip_decomp_build_kernel(const double* w, int n_freq, const double* taus, i
   if (!w || !taus || !K || n_freq <= 0 || n_tau <= 0) return fail(BISIP_ERR_BAD_ARG, "bisip_decomp_build_kernel: bad argument");
   DeviceGuard guard(K);
   build_kernel_matrix<<<ceil_div(n_freq * n_tau, 256), 256, 0, (cudaStream_t)stream>>>(w, n_freq, taus, n_tau, c_exp, K);
+  BISIP_CUDA(cudaGetLastError());
+  count_launches(1);
+  return BISIP_OK;
+}
+
+int bisip_gauss_loglike(const double* Z, const double* y, const double* yerr, int n_freq, int n_rows, double* ll_out,
+                        void* stream) {
+  if (!Z || !y || !yerr || !ll_out || n_freq <= 0 || n_rows <= 0) return fail(BISIP_ERR_BAD_ARG, "bisip_gauss_loglike: bad argument");
+  DeviceGuard guard(Z);
+  gauss_loglike_kernel<<<ceil_div(n_rows, 4), 128, 0, (cudaStream_t)stream>>>(Z, y, yerr, 2 * n_freq, n_rows, ll_out);
   BISIP_CUDA(cudaGetLastError());
   count_launches(1);
   return BISIP_OK;

@@ -16,6 +16,12 @@ namespace bisip {
 #ifndef BISIP_WP_SHIN_REGS
 #define BISIP_WP_SHIN_REGS 80
 #endif
+#ifndef BISIP_WP_CC1_REGS
+#define BISIP_WP_CC1_REGS 64
+#endif
+#ifndef BISIP_WP_CC2_REGS
+#define BISIP_WP_CC2_REGS 80
+#endif
 using DiasEval = VecWarpEvaluator<DiasRow, BISIP_WP_DIAS_ILP>;
 using ShinEval = VecWarpEvaluator<ShinRow, BISIP_WP_SHIN_ILP>;
 
@@ -29,8 +35,8 @@ int launch_ens_wp_vec(const EnsembleParams& P, dim3 grid, cudaStream_t st) {
       return launch_wp<ShinEval, BISIP_WP_SHIN_REGS>(P, grid, other + ShinEval::smem_doubles(P.d, rp) * 8, st, "ensemble_wp_shin");
     default:
       if (P.d.n_modes == 1)
-        return launch_wp<VecWarpEvaluator<ColeColeRowT<1>>, 64>(P, grid, other + VecWarpEvaluator<ColeColeRowT<1>>::smem_doubles(P.d, rp) * 8, st, "ensemble_wp_colecole");
-      return launch_wp<VecWarpEvaluator<ColeColeRowT<2>>, 80>(P, grid, other + VecWarpEvaluator<ColeColeRowT<2>>::smem_doubles(P.d, rp) * 8, st, "ensemble_wp_colecole");
+        return launch_wp<VecWarpEvaluator<ColeColeRowT<1>>, BISIP_WP_CC1_REGS>(P, grid, other + VecWarpEvaluator<ColeColeRowT<1>>::smem_doubles(P.d, rp) * 8, st, "ensemble_wp_colecole");
+      return launch_wp<VecWarpEvaluator<ColeColeRowT<2>>, BISIP_WP_CC2_REGS>(P, grid, other + VecWarpEvaluator<ColeColeRowT<2>>::smem_doubles(P.d, rp) * 8, st, "ensemble_wp_colecole");
   }
 }
 

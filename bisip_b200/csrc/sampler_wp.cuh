@@ -295,41 +295,11 @@ struct VecWarpEvaluator {
     constexpr int lpr = 2, stride = lpr * kFq;
     Row rr;
     rr.load(sm.rowc + (size_t)(row < nrows ? row : row0) * Row::kRC, n_modes);
-    double acc[ILP];
-#pragma unroll
-    for (int e = 0; e < ILP; ++e) acc[e] = 0.0;
     const double* f = sm.fq + sub * kFq;
-    int j = row < nrows ? sub : N;                               // rows beyond the half-step: no work
-    for (; j + (ILP - 1) * lpr < N; j += ILP * lpr, f += ILP * stride) {
-      double zre[ILP], zim[ILP];
-      bool ok = true;
-#pragma unroll
-      for (int e = 0; e < ILP; ++e) ok = ok & rr.template eval<true>(f + e * stride, zre[e], zim[e]);
-      if (!ok) {                               // rare: a reciprocal left the fast path's range
-#pragma unroll
-        for (int e = 0; e < ILP; ++e) rr.template eval<false>(f + e * stride, zre[e], zim[e]);
-      }
-#pragma unroll
-      for (int e = 0; e < ILP; ++e) {
-        const double2 a = lds2(f + e * stride + 4), b = lds2(f + e * stride + 6);
-        const double r0 = fma(-zre[e], a.y, a.x);     // (y - Z)/sigma
-        const double r1 = fma(-zim[e], b.y, b.x);
-        acc[e] = fma(r0, r0, acc[e]);
-        acc[e] = fma(r1, r1, acc[e]);
-      }
-    }
-    for (; j < N; j += lpr, f += stride) {
-      double zre, zim;
-      rr.template eval<false>(f, zre, zim);
-      const double2 a = lds2(f + 4), b = lds2(f + 6);
-      const double r0 = fma(-zre, a.y, a.x);
-      const double r1 = fma(-zim, b.y, b.x);
-      acc[0] = fma(r0, r0, acc[0]);
-      acc[0] = fma(r1, r1, acc[0]);
-    }
-    double tot = acc[0];
-#pragma unroll
-    for (int e = 1; e < ILP; ++e) tot += acc[e];
+    const int j0 = row < nrows ? sub : N;                        // rows beyond the half-step: no work
+    bool ok = true;
+    double tot = vec_row_chi<Row, ILP, true>(rr, f, j0, N, lpr, stride, ok);
+    if (!ok) tot = vec_row_chi<Row, 1, false>(rr, f, j0, N, lpr, stride, ok);    // rare: see vec_row_chi
     tot += __shfl_xor_sync(0xffffffffu, tot, 1);
     return tot;
   }

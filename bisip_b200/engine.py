@@ -93,6 +93,19 @@ def log_probability(spec, theta, w, y, yerr, bounds):
     return lp
 
 
+def gauss_loglike(Z, y, yerr):
+    """Z (n, 2, N) caller-supplied model rows; y, yerr (2, N) -> ll (n,).
+    Reference: Inversion._log_likelihood with a user callable (models.py:59-62)."""
+    lib = _lib.load()
+    _chk_cuda_f64(Z, y, yerr)
+    n, N = Z.shape[0], Z.shape[-1]
+    ll = torch.empty((n,), dtype=torch.float64, device=Z.device)
+    rc = lib.bisip_gauss_loglike(_lib.ptr(Z), _lib.ptr(y), _lib.ptr(yerr), N, n, _lib.ptr(ll),
+                                 _lib.stream_ptr(Z.device))
+    _lib.check(rc, "bisip_gauss_loglike")
+    return ll
+
+
 def decomp_kernel_matrix(w, taus, c_exp):
     """K (S, 2N) = 1 - 1/(1+(i w tau)^c): columns [real | imag]."""
     lib = _lib.load()

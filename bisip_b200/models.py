@@ -60,10 +60,26 @@ class Inversion(_plotlib.plotlib, _utils.utils):
         single = th.ndim == 1
         return _lib.dev_f64(th.reshape(1, -1, th.shape[-1]), dev), single
 
-    def _require_own_forward(self, f):
-        if getattr(f, '__self__', None) is not self or getattr(f, '__func__', None) is not type(self).forward:
-            raise NotImplementedError('only the built-in forward models have CUDA kernels; '
-                                      'bisip_b200 has no CPU fallback for a user callable')
+    def _is_own_forward(self, f):
+        return getattr(f, '__self__', None) is self and getattr(f, '__func__', None) is type(self).forward
+
+    def _user_loglike(self, theta, f, x, y, yerr):
+        """``_log_likelihood`` for a user-supplied forward callable (reference ``models.py:59-62`` accepts any
+        ``f(theta, x) -> (2, N)``): the callable runs where the user wrote it, on the host, once per parameter vector;
+        the Gaussian reduction runs on the GPU (``bisip_gauss_loglike``).  There is still no CPU implementation of
+        the likelihood or of the built-in models."""
+        dev = _lib.require_cuda(self.device)
+        th = np.asarray(theta, dtype=np.float64)
+        single = th.ndim == 1
+        rows = [np.asarray(f(t, x), dtype=np.float64) for t in th.reshape(-1, th.shape[-1])]
+        shape = np.shape(y)
+        for r in rows:
+            if r.shape != shape:
+                raise ValueError(f'forward callable returned shape {r.shape}, data has shape {shape}')
+        Z = _lib.dev_f64(np.stack(rows).reshape(len(rows), 2, -1), dev)
+        ll = engine.gauss_loglike(Z, _lib.dev_const(y, dev).reshape(2, -1),
+                                  _lib.dev_const(yerr, dev).reshape(2, -1)).cpu().numpy()
+        return float(ll[0]) if single else ll.reshape(th.shape[:-1])
 
     # ---------------------------------------------------------------- probabilities
     def forward(self, theta, w):
@@ -77,7 +93,15 @@ class Inversion(_plotlib.plotlib, _utils.utils):
     def _log_probability(self, theta, model, bounds, x, y, yerr):
         """Bayes numerator: strict box prior + Gaussian log-likelihood, fused on the GPU
         (reference ``models.py:71-76``)."""
-        self._require_own_forward(model)
+        if not self._is_own_forward(model):      # user callable: prior on the host, callable on the host, reduction on the GPU
+            lp = self._log_prior(theta, bounds)
+            if np.ndim(lp) == 0:
+                return -np.inf if not np.isfinite(lp) else lp + self._log_likelihood(theta, model, x, y, yerr)
+            out = np.full(np.shape(lp), -np.inf)
+            ok = np.isfinite(lp)
+            if ok.any():
+                out[ok] = self._user_loglike(np.asarray(theta, dtype=np.float64)[ok], model, x, y, yerr)
+            return out
         dev = _lib.require_cuda(self.device)
         th, single = self._theta_batch(theta, dev)
         lp = engine.log_probability(self._spec(dev), th, _lib.dev_const(x, dev),
@@ -88,6 +112,8 @@ class Inversion(_plotlib.plotlib, _utils.utils):
 
     def _log_likelihood(self, theta, f, x, y, yerr):
         """-0.5*sum((y-f)^2/sigma^2 + 2 ln sigma^2) (reference ``models.py:59-62``)."""
+        if not self._is_own_forward(f):
+            return self._user_loglike(theta, f, x, y, yerr)
         wide = np.array([[-np.inf] * len(self.params), [np.inf] * len(self.params)])
         return self._log_probability(theta, f, wide, x, y, yerr)
 

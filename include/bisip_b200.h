@@ -119,6 +119,12 @@ int bisip_log_probability(const bisip_model_desc *desc, int n_spectra, int n_the
                           const double *y, const double *yerr, const double *bounds,
                           double *lp_out, void *stream);
 
+/* Gaussian log-likelihood of caller-supplied model rows (the reference's `_log_likelihood(theta, f, x, y, yerr)` with a
+ * user callable `f`, models.py:59-62: the callable runs where the user wrote it, on the host; the reduction runs here):
+ *   ll_out[r] = -0.5*sum_c((y[c]-Z[r][c])^2/yerr[c]^2 + 2*ln(yerr[c]^2)),  Z [n_rows][2*n_freq], y / yerr [2*n_freq]. */
+int bisip_gauss_loglike(const double *Z, const double *y, const double *yerr, int n_freq, int n_rows,
+                        double *ll_out, void *stream);
+
 /* Decomposition kernel matrix K[n_tau][2*n_freq] = 1 - 1/(1 + (i w tau)^c): columns
  * [0,N) real parts, [N,2N) imaginary parts. */
 int bisip_decomp_build_kernel(const double *w, int n_freq, const double *taus, int n_tau,

@@ -230,3 +230,44 @@ def test_tcgen05_dispatch_and_agreement(N, S, P, W, c_exp, prec, kind):
     res = {p: inv[p].fit(p0=p0.copy(), discard=30, thin=1) for p in inv}
     assert np.all(res[prec]['flags'] == 0)
     assert np.abs(res[prec]['acceptance_fraction'] - res['fp64']['acceptance_fraction']).max() < 0.1
+
+
+@pytest.mark.gpu
+def test_user_forward_callable(data_files):
+    """The reference's _log_likelihood / _log_probability take ANY forward callable (models.py:59-62, :71-76): the
+    callable runs on the host, the Gaussian reduction in bisip_gauss_loglike; tolerance 1e-12 relative against the
+    reference expression evaluated in NumPy on the same model rows."""
+    import bisip_b200 as bb
+    m = bb.PeltonColeCole(data_files['SIP-K389175'], nwalkers=32, nsteps=10, n_modes=1)
+    w, y, yerr = m.data['w'], m.data['zn'], m.data['zn_err']
+    calls = []
+
+    def debye(theta, x):               # a model the library does not have
+        calls.append(1)
+        z = theta[0] * (1 - theta[1] * (1 - 1 / (1 + 1j * x * 10.0 ** theta[2])))
+        return np.array([z.real, z.imag])
+
+    def ref_ll(theta):
+        s2 = yerr ** 2
+        return -0.5 * np.sum((y - debye(theta, w)) ** 2 / s2 + 2 * np.log(s2))
+
+    rng = np.random.default_rng(5)
+    lo, hi = m.param_bounds
+    th = rng.uniform(lo, hi, (7, 4))
+    want = np.array([ref_ll(t) for t in th])
+    got = m._log_likelihood(th, debye, w, y, yerr)
+    assert got.shape == (7,)
+    np.testing.assert_allclose(got, want, rtol=1e-12)
+    one = m._log_likelihood(th[0], debye, w, y, yerr)
+    assert isinstance(one, float) and abs(one - want[0]) <= 1e-12 * abs(want[0])
+    # prior first: outside (or on a face of) the box the callable is never run
+    th[2, 1] = hi[1]
+    th[5, 0] = lo[0] - 1.0
+    calls.clear()
+    lp = m._log_probability(th, debye, m.param_bounds, w, y, yerr)
+    assert len(calls) == 5 and np.isneginf(lp[[2, 5]]).all()
+    keep = [0, 1, 3, 4, 6]
+    np.testing.assert_allclose(lp[keep], want[keep], rtol=1e-12)
+    assert m._log_probability(th[2], debye, m.param_bounds, w, y, yerr) == -np.inf
+    with pytest.raises(ValueError):
+        m._log_likelihood(th[0], lambda t, x: np.zeros(3), w, y, yerr)

@@ -80,8 +80,14 @@ def test_no_cpu_fallback(data_files):
         m.forward(np.array([1.0, 0.25, -10, 5, 0.5]), m.data['w'])
     with pytest.raises(BisipError):
         m.fit()
-    with pytest.raises(NotImplementedError):
-        m._log_probability(np.zeros(5), lambda t, w: 0, m.param_bounds, m.data['w'], m.data['zn'], m.data['zn_err'])
+    # a user forward callable runs on the host, but the likelihood reduction is a CUDA kernel: still no CPU path
+    inside = m.param_bounds.mean(axis=0)
+    with pytest.raises(BisipError, match='no CPU fallback'):
+        m._log_probability(inside, lambda t, w: np.zeros((2, len(w))), m.param_bounds, m.data['w'], m.data['zn'],
+                           m.data['zn_err'])
+    # outside the prior box the reference returns -inf without calling the model (models.py:71-76)
+    assert m._log_probability(np.zeros(5), lambda t, w: 1 / 0, m.param_bounds, m.data['w'], m.data['zn'],
+                              m.data['zn_err']) == -np.inf
 
 
 def test_product_never_imports_oracle():

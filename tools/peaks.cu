@@ -134,6 +134,55 @@ template <int SHAPE> double layout_err() {
   return e;
 }
 
+
+// `peaks --mix`: does an FP64 instruction cost ONE issue slot (and two cycles of its half-rate pipe) or does it hold the
+// warp scheduler's dispatch port for both cycles?  8 independent DFMA chains per thread, interleaved with NI independent
+// integer instructions per DFMA (KIND 0: IMAD, 1: SHF rotate-by-self, 2: shared-memory load).  If the companion
+// instructions hide in the DFMA's second cycle the DFMA rate stays at peak for NI = 1; if the port is held it drops to 2/3.
+template <int NI, int KIND>
+__global__ void k_mix(double* out, int iters, double s, unsigned m, unsigned c) {
+  __shared__ unsigned sh[256];
+  sh[threadIdx.x & 255] = c;
+  __syncthreads();
+  double acc[8];
+  unsigned x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { acc[i] = threadIdx.x + i; x[i] = threadIdx.x * 8 + i; }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[i] = fma(acc[i], s, 1e-9);
+#pragma unroll
+      for (int k = 0; k < NI; ++k) {
+        if (KIND == 0) asm volatile("mad.lo.u32 %0, %0, %0, %1;" : "+r"(x[i]) : "r"(c));
+        if (KIND == 1) asm volatile("shf.l.wrap.b32 %0, %0, %0, %0;" : "+r"(x[i]));
+        if (KIND == 2) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(&sh[(x[i] + k) & 255]))); x[i] ^= v; }
+      }
+    }
+  }
+  double r = 0; unsigned xs = 0;
+  for (int i = 0; i < 8; ++i) { r += acc[i]; xs += x[i]; }
+  if (r == 123.456 || xs == 0x12345u) out[0] = r + xs;
+}
+
+template <int NI, int KIND> static double mix_rate(double* dout, int sms, int iters) {
+  const int grid = sms * 8, blk = 256;
+  double ms = time_ms([&] { k_mix<NI, KIND><<<grid, blk>>>(dout, iters, 1.0000001, 3u, 7u); });
+  return 2.0 * 8 * iters * (double)grid * blk / ms / 1e9;      // DFMA TFLOP/s
+}
+static int mix() {
+  cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
+  int sms = p.multiProcessorCount;
+  double* dout; CK(cudaMalloc(&dout, 64));
+  const int iters = 10000;
+  printf("{\"gpu\": \"%s\", \"what\": \"DFMA TFLOP/s with NI companion instructions per DFMA\"", p.name);
+  printf(", \"imad\": [%.2f, %.2f, %.2f, %.2f]", mix_rate<0, 0>(dout, sms, iters), mix_rate<1, 0>(dout, sms, iters), mix_rate<2, 0>(dout, sms, iters), mix_rate<3, 0>(dout, sms, iters));
+  printf(", \"shf\": [%.2f, %.2f, %.2f, %.2f]", mix_rate<0, 1>(dout, sms, iters), mix_rate<1, 1>(dout, sms, iters), mix_rate<2, 1>(dout, sms, iters), mix_rate<3, 1>(dout, sms, iters));
+  printf(", \"lds\": [%.2f, %.2f, %.2f]", mix_rate<0, 2>(dout, sms, iters), mix_rate<1, 2>(dout, sms, iters), mix_rate<2, 2>(dout, sms, iters));
+  printf("}\n");
+  return 0;
+}
+
 #include <chrono>
 #include <cstring>
 // `peaks --sustain SEC`: run the m16n8k16 DMMA kernel back to back for SEC seconds (the regime of a
@@ -166,6 +215,7 @@ static int sustain(double seconds) {
 
 int main(int argc, char** argv) {
   if (argc >= 3 && !strcmp(argv[1], "--sustain")) return sustain(atof(argv[2]));
+  if (argc >= 2 && !strcmp(argv[1], "--mix")) return mix();
   cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
   int sms = p.multiProcessorCount;
   double* dout; CK(cudaMalloc(&dout, 64)); float* fout = (float*)dout;
