@@ -234,12 +234,16 @@ int bisip_ensemble_run(const bisip_model_desc* desc, int n_spectra, int n_walker
         return launch_ens_wp_collapsed(P, grid, st);
       if (desc->model == BISIP_MODEL_DECOMP && desc->precision == BISIP_PREC_FP64 && desc->n_tau > 32 && desc->n_tau <= 64)
         return launch_ens_wp_dmma(P, grid, st);
-      // measured (profiles/r02_wp_sweep.md): warp-private wins by 1.2-2x for <= 64 walkers or short spectra and for
-      // Cole-Cole everywhere; for Dias / Shin with > 64 walkers and > 32 frequencies the block-synchronous kernel is
-      // 2-6 % faster (its serial phases run on full warps; the long frequency loop dominates either way)
-      const bool long_vec = n_walkers > 64 && desc->n_freq > 32;
-      if ((desc->model == BISIP_MODEL_DIAS || desc->model == BISIP_MODEL_SHIN) ? !long_vec
-                                                                               : (desc->model == BISIP_MODEL_COLECOLE && desc->n_modes <= 2))
+      // measured (profiles/r02_wp_sweep.md, r02c_vec_analysis.md): warp-private wins by 1.2-2x for <= 64 walkers or short
+      // spectra and for 1-mode Cole-Cole everywhere; for Dias / Shin / 2-mode Cole-Cole with > 64 walkers and > 32
+      // frequencies the block-synchronous kernel is 2-7 % faster (its serial phases run on full warps; the long frequency
+      // loop dominates either way).  BISIP_SAMPLER=wp forces the warp-private kernel there (developer comparison).
+      const bool force_wp = e && !strcmp(e, "wp");
+      const bool long_vec = n_walkers > 64 && desc->n_freq > 32 && !force_wp;
+      const bool wp_vec = desc->model == BISIP_MODEL_DIAS || desc->model == BISIP_MODEL_SHIN
+                              ? !long_vec
+                              : desc->model == BISIP_MODEL_COLECOLE && (desc->n_modes == 1 || (desc->n_modes == 2 && !long_vec));
+      if (wp_vec)
         return launch_ens_wp_vec(P, grid, st);
     }
   }

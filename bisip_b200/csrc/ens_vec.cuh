@@ -16,11 +16,11 @@ constexpr int kMinBVec = 4;      // 256-thread CTAs, 64 registers
 constexpr int kVecSmallW = 128;  // walkers up to which the 128-thread variant is used
 
 // launch ensemble_kernel<VecEvaluator<Row>> in the shape picked for W walkers; MB128 = CTAs/SM of the
-// 128-thread variant (8 -> 64 registers, 6 -> 80 registers)
-template <class Row, int MB128>
+// 128-thread variant (8 -> 64 registers, 6 -> 80 registers), ILP128 = its frequencies in flight per thread
+template <class Row, int MB128, int ILP128 = 2>
 int launch_vec_ensemble(const EnsembleParams& P, dim3 grid, size_t smem, cudaStream_t st, const char* name) {
   if (P.W <= kVecSmallW)
-    return launch(ensemble_kernel<VecEvaluator<Row>, MB128, 128>, grid, smem, st, name, &P, 128);
+    return launch(ensemble_kernel<VecEvaluator<Row, ILP128>, MB128, 128>, grid, smem, st, name, &P, 128);
   return launch(ensemble_kernel<VecEvaluator<Row>, kMinBVec, kThreads>, grid, smem, st, name, &P, kThreads);
 }
 

@@ -3,12 +3,12 @@
 
 namespace bisip {
 
-// developer knobs (defaults = the measured best, profiles/r02_vec_tuning.md)
+// developer knobs (defaults = the measured best: profiles/r02_wp_sweep.md, r02c_vec_analysis.md)
 #ifndef BISIP_WP_DIAS_ILP
-#define BISIP_WP_DIAS_ILP 2
+#define BISIP_WP_DIAS_ILP 4
 #endif
 #ifndef BISIP_WP_DIAS_REGS
-#define BISIP_WP_DIAS_REGS 64
+#define BISIP_WP_DIAS_REGS 80
 #endif
 #ifndef BISIP_WP_SHIN_ILP
 #define BISIP_WP_SHIN_ILP 2
@@ -17,7 +17,7 @@ namespace bisip {
 #define BISIP_WP_SHIN_REGS 80
 #endif
 #ifndef BISIP_WP_CC1_REGS
-#define BISIP_WP_CC1_REGS 64
+#define BISIP_WP_CC1_REGS 80
 #endif
 #ifndef BISIP_WP_CC2_REGS
 #define BISIP_WP_CC2_REGS 80

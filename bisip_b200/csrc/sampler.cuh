@@ -584,7 +584,7 @@ struct DecompCollapsedEvaluator {
   }
 };
 
-template <class Row>
+template <class Row, int ILP = 2>
 struct VecEvaluator {
   static constexpr bool kClustered = false;
   static constexpr bool kNeedsPrepare = true;
@@ -609,7 +609,7 @@ struct VecEvaluator {
   __device__ __forceinline__ void release() {}
   __device__ void eval_chi(const double*, int, int nrows, double* chi, RankSide& side) {
     side.finish();
-    vec_eval_chi<Row>(sm, N, n_modes, nrows, chi);
+    vec_eval_chi<Row, ILP>(sm, N, n_modes, nrows, chi);
   }
 };
 

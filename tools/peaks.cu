@@ -165,6 +165,45 @@ __global__ void k_mix(double* out, int iters, double s, unsigned m, unsigned c) 
   if (r == 123.456 || xs == 0x12345u) out[0] = r + xs;
 }
 
+
+// `peaks --mix` part 2: FP64 rate by operand pattern.  The peak loop above feeds DFMA one register pair (acc) + a uniform
+// register + an immediate; real code reads three register pairs per DFMA.  MODE 1: acc = fma(acc, b_i, c_i) with b_i, c_i
+// in distinct registers; 2: acc = fma(b_i, c_i, acc); 3: DMUL acc * b_i; 4: DADD acc + b_i; 5: two-chain mix
+// d = fma(a, b, c) where a, b, c are all results of other chains (the shape of the model loops).
+__constant__ double kDopConst[8] = {1e-9, 2e-9, 3e-9, 4e-9, 5e-9, 6e-9, 7e-9, 8e-9};
+template <int MODE>
+__global__ void k_dop(double* out, const double* __restrict__ in, int iters) {
+  double acc[8], b[8], c[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { acc[i] = threadIdx.x + i; b[i] = in[threadIdx.x * 16 + i]; c[i] = in[threadIdx.x * 16 + 8 + i]; }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (MODE == 1) acc[i] = fma(acc[i], b[i], c[i]);
+      if (MODE == 2) acc[i] = fma(b[i], c[i], acc[i]);
+      if (MODE == 3) acc[i] = acc[i] * b[i];
+      if (MODE == 4) acc[i] = acc[i] + c[i];
+      if (MODE == 5) acc[i] = fma(acc[(i + 3) & 7], b[i], acc[(i + 5) & 7]);
+      if (MODE == 6) acc[i] = fma(c[i], c[i], acc[i]);          // the same register twice + one more
+      if (MODE == 7) acc[i] = fma(acc[i], b[i], acc[i]);
+      if (MODE == 8) acc[i] = fma(acc[i], b[i], kDopConst[i]);  // two registers + a constant-bank operand
+    }
+  }
+  double r = 0;
+  for (int i = 0; i < 8; ++i) r += acc[i];
+  if (r == 123.456) out[0] = r;
+}
+template <int MODE> static double dop_rate(double* dout, int sms, int iters) {
+  const int grid = sms * 8, blk = 256;
+  static double* din = nullptr;
+  if (!din) {
+    std::vector<double> h(256 * 16);
+    for (int t = 0; t < 256; ++t) for (int i = 0; i < 16; ++i) h[t * 16 + i] = i < 8 ? 1.0000001 + 1e-12 * (t + i) : 1e-9 * (1 + i + t);
+    CK(cudaMalloc(&din, h.size() * 8)); CK(cudaMemcpy(din, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
+  }
+  double ms = time_ms([&] { k_dop<MODE><<<grid, blk>>>(dout, din, iters); });
+  return 8.0 * iters * (double)grid * blk / ms / 1e9;      // 1e12 FP64 thread-instructions per second
+}
 template <int NI, int KIND> static double mix_rate(double* dout, int sms, int iters) {
   const int grid = sms * 8, blk = 256;
   double ms = time_ms([&] { k_mix<NI, KIND><<<grid, blk>>>(dout, iters, 1.0000001, 3u, 7u); });
@@ -179,6 +218,10 @@ static int mix() {
   printf(", \"imad\": [%.2f, %.2f, %.2f, %.2f]", mix_rate<0, 0>(dout, sms, iters), mix_rate<1, 0>(dout, sms, iters), mix_rate<2, 0>(dout, sms, iters), mix_rate<3, 0>(dout, sms, iters));
   printf(", \"shf\": [%.2f, %.2f, %.2f, %.2f]", mix_rate<0, 1>(dout, sms, iters), mix_rate<1, 1>(dout, sms, iters), mix_rate<2, 1>(dout, sms, iters), mix_rate<3, 1>(dout, sms, iters));
   printf(", \"lds\": [%.2f, %.2f, %.2f]", mix_rate<0, 2>(dout, sms, iters), mix_rate<1, 2>(dout, sms, iters), mix_rate<2, 2>(dout, sms, iters));
+  printf(", \"fp64_tinst_per_s_e12\": {\"peak_loop\": %.2f, \"fma_acc_r_r\": %.2f, \"fma_r_r_acc\": %.2f, \"mul_acc_r\": %.2f, \"add_acc_r\": %.2f, \"fma_cross_chain\": %.2f, \"fma_r_r_acc_same_r\": %.2f, \"fma_acc_r_acc\": %.2f, \"fma_acc_r_constbank\": %.2f}",
+         mix_rate<0, 0>(dout, sms, iters) / 2, dop_rate<1>(dout, sms, iters), dop_rate<2>(dout, sms, iters), dop_rate<3>(dout, sms, iters),
+         dop_rate<4>(dout, sms, iters), dop_rate<5>(dout, sms, iters), dop_rate<6>(dout, sms, iters), dop_rate<7>(dout, sms, iters),
+         dop_rate<8>(dout, sms, iters));
   printf("}\n");
   return 0;
 }
