@@ -356,9 +356,9 @@ __device__ inline void decomp_umma_init(DecompUmmaSmem& s, const DecompUmmaShape
 // All TMEM traffic of this CTA is complete (callers end their last evaluation with a barrier).
 __device__ inline void decomp_umma_release(DecompUmmaSmem& s, const DecompUmmaShape& sh) {
 #ifdef BISIP_PHASE_TIMING
-  if (blockIdx.x == 0 && threadIdx.x == 0 && gridDim.y == 1 && s.ph[3] > 100000)
+  if (blockIdx.x == 0 && threadIdx.x == 0 && gridDim.y == 1 && s.ph[2] + s.ph[4] > 100000)
     printf("umma eval cycles (thread 0, whole run): b=R.a %lld  split+st %lld  wait-st+barrier %lld | mma1-wait %lld  repack+barrier %lld  "
-           "mma2-wait %lld  epilogue %lld  tail %lld\n", s.ph[6], s.ph[7], s.ph[0], s.ph[1], s.ph[2], s.ph[3], s.ph[4], s.ph[5]);
+           "mma2-issue(warp 7 only) %lld  mma2-wait+epilogue %lld  tail %lld\n", s.ph[6], s.ph[7], s.ph[0], s.ph[1], s.ph[2], s.ph[3], s.ph[4], s.ph[5]);
 #endif
   tc_fence_before();
   __syncthreads();

@@ -204,6 +204,32 @@ template <int MODE> static double dop_rate(double* dout, int sms, int iters) {
   double ms = time_ms([&] { k_dop<MODE><<<grid, blk>>>(dout, din, iters); });
   return 8.0 * iters * (double)grid * blk / ms / 1e9;      // 1e12 FP64 thread-instructions per second
 }
+
+// dependent-issue latency (one warp, one chain, clock64 around 4096 dependent instructions)
+template <int KIND>
+__global__ void k_lat(double* out, long long* cyc, double s, float sf, unsigned m) {
+  double a = threadIdx.x + 1.0; float f = threadIdx.x + 1.0f; unsigned x = threadIdx.x + 1u;
+  long long t0 = clock64();
+#pragma unroll 64
+  for (int i = 0; i < 4096; ++i) {
+    if (KIND == 0) a = fma(a, s, 1e-9);
+    if (KIND == 1) f = fmaf(f, sf, 1e-9f);
+    if (KIND == 2) asm volatile("mad.lo.u32 %0, %0, %0, %1;" : "+r"(x) : "r"(m));
+    if (KIND == 3) a = a * s;
+    if (KIND == 4) a = a + s;
+  }
+  long long t1 = clock64();
+  if (threadIdx.x == 0) cyc[0] = t1 - t0;
+  if (a == 123.456 || f == 123.456f || x == 0x12345u) out[0] = a + f + x;
+}
+template <int KIND> static double lat_cycles(double* dout) {
+  static long long* dc = nullptr;
+  if (!dc) CK(cudaMalloc(&dc, 8));
+  k_lat<KIND><<<1, 32>>>(dout, dc, 1.0000001, 1.0000001f, 3u); CK(cudaDeviceSynchronize());
+  k_lat<KIND><<<1, 32>>>(dout, dc, 1.0000001, 1.0000001f, 3u); CK(cudaDeviceSynchronize());
+  long long h; CK(cudaMemcpy(&h, dc, 8, cudaMemcpyDeviceToHost));
+  return h / 4096.0;
+}
 template <int NI, int KIND> static double mix_rate(double* dout, int sms, int iters) {
   const int grid = sms * 8, blk = 256;
   double ms = time_ms([&] { k_mix<NI, KIND><<<grid, blk>>>(dout, iters, 1.0000001, 3u, 7u); });
@@ -222,6 +248,8 @@ static int mix() {
          mix_rate<0, 0>(dout, sms, iters) / 2, dop_rate<1>(dout, sms, iters), dop_rate<2>(dout, sms, iters), dop_rate<3>(dout, sms, iters),
          dop_rate<4>(dout, sms, iters), dop_rate<5>(dout, sms, iters), dop_rate<6>(dout, sms, iters), dop_rate<7>(dout, sms, iters),
          dop_rate<8>(dout, sms, iters));
+  printf(", \"dependent_latency_cycles\": {\"dfma\": %.1f, \"dmul\": %.1f, \"dadd\": %.1f, \"ffma\": %.1f, \"imad\": %.1f}",
+         lat_cycles<0>(dout), lat_cycles<3>(dout), lat_cycles<4>(dout), lat_cycles<1>(dout), lat_cycles<2>(dout));
   printf("}\n");
   return 0;
 }
