@@ -403,3 +403,33 @@ def test_batch_validation_and_run_mcmc_kwargs(monkeypatch):
     s = EnsembleSampler(16, 5, engine.ModelSpec(model=_lib.MODEL_DIAS, ndim=5), w, zn[0], ze[0], np.zeros((2, 5)), seed=1)
     with pytest.raises(NotImplementedError, match='thin_by'):
         s.run_mcmc(np.zeros((16, 5)), 10, thin_by=2)
+
+
+def test_exp_table_constants_and_accuracy():
+    """The table-driven exp of csrc/models.cuh (exp_fast): every 2^(j/32) entry in the source is the correctly rounded
+    value, the reduction / Taylor constants are the ones tools/exp_table_check.py evaluates, and that evaluation (exact
+    rational arithmetic, one rounding per FMA) stays below 2e-16 relative — far inside the 1e-12 parity bar."""
+    import importlib.util
+    import re
+    from decimal import Decimal, getcontext
+    src = open(os.path.join(ROOT, 'bisip_b200', 'csrc', 'models.cuh')).read()
+    tab = re.search(r'kExp2Tab\[32\] = \{(.*?)\};', src, re.S).group(1)
+    vals = [float.fromhex(t) for t in re.findall(r'0x1\.[0-9a-f]+p[+-]\d+', tab)]
+    assert len(vals) == 32
+    getcontext().prec = 50
+    ln2 = Decimal(2).ln()
+    for j, v in enumerate(vals):
+        assert v == float((ln2 * Decimal(j) / Decimal(32)).exp()), j
+    spec = importlib.util.spec_from_file_location('exp_table_check', os.path.join(ROOT, 'tools', 'exp_table_check.py'))
+    chk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(chk)
+    kt = re.search(r'kExpT\[8\] = \{(.*?)\};', src, re.S).group(1)
+    consts = [float.fromhex(t) for t in re.findall(r'-?0x1\.[0-9a-f]+p[+-]\d+', kt)]
+    assert consts == [chk.A, chk.H, chk.L] + chk.C
+    assert chk.TAB == vals
+    rng = np.random.default_rng(3)
+    worst = 0.0
+    for x in np.concatenate([rng.uniform(-700, 700, 300), rng.uniform(-40, 40, 300), [0.0, 1e-300, -1e-9, 699.9, -699.9]]):
+        ex = Decimal(float(x)).exp()
+        worst = max(worst, float(abs((Decimal(chk.exp_table(float(x))) - ex) / ex)))
+    assert worst < 2e-16
