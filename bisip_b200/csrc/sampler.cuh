@@ -334,20 +334,14 @@ struct RankSide {
 // on average).  rank = bin start + smaller keys in the bin — the same number the all-pairs count above produces, so
 // chains stay bit-identical; the shared-memory atomics only decide where a key is parked inside its bin.
 // All threads of the CTA; W <= NT.  Ends without a barrier (the caller synchronises before list_out is read).
+// ZERO = false: the caller has zeroed hist[0, 256) behind a barrier already (the sampling loop does it in the first
+// accept phase of the step, which saves one CTA barrier per step).
+// rank_binned_rest: everything after the bin slots (key, bin, slot of this thread's walker, taken with atomicAdd on
+// counters that were zero; a barrier lies between the last atomicAdd and this call): scan, placement, count.
 template <int NT>
-__device__ __forceinline__ void rank_keys_binned(const uint32_t* __restrict__ keys, int* __restrict__ list_out, int W,
-                                                 int* __restrict__ hist, uint32_t* __restrict__ sorted) {
+__device__ __forceinline__ void rank_binned_rest(int* __restrict__ list_out, int W, int* __restrict__ hist,
+                                                 uint32_t* __restrict__ sorted, uint32_t key, int bin, int slot) {
   const int tid = threadIdx.x;
-  for (int i = tid; i < 256; i += NT) hist[i] = 0;
-  __syncthreads();
-  uint32_t key = 0;
-  int bin = 0, slot = 0;
-  if (tid < W) {
-    key = keys[tid];
-    bin = (int)(key >> 24);
-    slot = atomicAdd(&hist[bin], 1);
-  }
-  __syncthreads();
   if (tid < 32) {                                  // exclusive scan of the 256 counters, 8 per lane
     int4* h4 = reinterpret_cast<int4*>(hist);
     const int4 a = h4[2 * tid], c = h4[2 * tid + 1];
@@ -377,6 +371,23 @@ __device__ __forceinline__ void rank_keys_binned(const uint32_t* __restrict__ ke
     for (int j = start; j < end; ++j) cnt += sorted[j] < key ? 1 : 0;
     list_out[start + cnt] = tid;
   }
+}
+
+template <int NT>
+__device__ __forceinline__ void rank_keys_binned(const uint32_t* __restrict__ keys, int* __restrict__ list_out, int W,
+                                                 int* __restrict__ hist, uint32_t* __restrict__ sorted) {
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 256; i += NT) hist[i] = 0;
+  __syncthreads();
+  uint32_t key = 0;
+  int bin = 0, slot = 0;
+  if (tid < W) {
+    key = keys[tid];
+    bin = (int)(key >> 24);
+    slot = atomicAdd(&hist[bin], 1);
+  }
+  __syncthreads();
+  rank_binned_rest<NT>(list_out, W, hist, sorted, key, bin, slot);
 }
 
 // Binned key ranking (rank_keys_binned above) cut at its barriers so that the warp-private sampler can place the pieces
@@ -443,6 +454,7 @@ __device__ __forceinline__ void rank_part_c(int W, const int* __restrict__ count
 template <int KC>
 struct DecompEvaluator {
   static constexpr bool kClustered = false;
+  static constexpr bool kRankInAccept = true;
   static constexpr bool kNeedsPrepare = false;
   __device__ __forceinline__ void prepare_row(int, const double*) {}
   __device__ __forceinline__ void release() {}
@@ -469,6 +481,7 @@ struct DecompEvaluator {
 // Large tau grids: stage 1 recomputed per k chunk, frequency columns split over a CTA cluster.
 struct DecompRCEvaluator {
   static constexpr bool kClustered = true;
+  static constexpr bool kRankInAccept = false;     // measured: 3.712e8 vs 3.691e8 at 256 taus (profiles/r02d_barriers.md)
   static constexpr bool kNeedsPrepare = false;
   __device__ __forceinline__ void prepare_row(int, const double*) {}
   __device__ __forceinline__ void release() {}
@@ -497,6 +510,7 @@ struct DecompRCEvaluator {
 template <int PREC>
 struct DecompTF32Evaluator {
   static constexpr bool kClustered = true;
+  static constexpr bool kRankInAccept = true;
   static constexpr bool kNeedsPrepare = false;
   __device__ __forceinline__ void prepare_row(int, const double*) {}
   __device__ __forceinline__ void release() {}
@@ -526,6 +540,7 @@ struct DecompTF32Evaluator {
 template <int PREC, bool CL = false>
 struct DecompUmmaEvaluator {
   static constexpr bool kClustered = CL;
+  static constexpr bool kRankInAccept = true;      // TF32 8.38e9 vs 8.32e9, 3xTF32 equal
   static constexpr bool kNeedsPrepare = false;
   __device__ __forceinline__ void prepare_row(int, const double*) {}
   DecompUmmaSmem sm;
@@ -552,6 +567,7 @@ struct DecompUmmaEvaluator {
 // Collapsed form z = (L K) a on the FP64 vector pipe (decomp_collapsed.cuh): precision 'fp64-collapsed'.
 struct DecompCollapsedEvaluator {
   static constexpr bool kClustered = false;
+  static constexpr bool kRankInAccept = true;
   static constexpr bool kNeedsPrepare = false;
   __device__ __forceinline__ void prepare_row(int, const double*) {}
   __device__ __forceinline__ void release() {}
@@ -587,6 +603,7 @@ struct DecompCollapsedEvaluator {
 template <class Row, int ILP = 2>
 struct VecEvaluator {
   static constexpr bool kClustered = false;
+  static constexpr bool kRankInAccept = Row::kRankInAccept;
   static constexpr bool kNeedsPrepare = true;
   VecSmem sm;
   int N, n_modes;
@@ -740,6 +757,15 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
   draw_rows(dctx, (uint32_t)P.step0, 0, tid, NT);
   __syncthreads();
 
+  uint32_t rk_key = 0;
+  int rk_bin = 0, rk_slot = 0;
+  // bin slots of the key ranking inside the second accept phase (one CTA barrier less per step) or in a phase of their
+  // own: +-1-2 % either way depending on the evaluator and the CTA size (profiles/r02d_barriers.md)
+#ifdef BISIP_RANK_IN_ACCEPT
+  constexpr bool kRankInAccept = BISIP_RANK_IN_ACCEPT != 0;
+#else
+  constexpr bool kRankInAccept = Eval::kRankInAccept && (NT == 128 || Eval::kClustered || !Eval::kNeedsPrepare);
+#endif
   PHASE_DECL
   for (int it = 0; it < P.nsteps; ++it) {
     const uint32_t t = (uint32_t)(P.step0 + it);
@@ -803,27 +829,49 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
         }
       }
       FINE_MARK(10)
-      if (sp == 0) gen_keys(t + 1u, tid, NT);
+      if (sp == 0) {
+        gen_keys(t + 1u, tid, NT);
+        if (binned)                                  // bin counters of the ranking at the end of this step (last read: the
+          for (int i = tid; i < 256; i += NT) s.hist[i] = 0;   // previous step's ranking, two barriers ago)
+      }
+      else if (binned && kRankInAccept) {
+        // second half-step: bin slot of this thread's key of the NEXT step's split (keys drawn and counters zeroed one
+        // half-step ago) — the first of the ranking's barriers is the one that ends this accept phase
+        rk_key = 0; rk_bin = 0; rk_slot = 0;
+        if (tid < W) {
+          rk_key = s.keys[tid];
+          rk_bin = (int)(rk_key >> 24);
+          rk_slot = atomicAdd(&s.hist[rk_bin], 1);
+        }
+      }
       FINE_MARK(11)
       __syncthreads();
       PHASE_MARK(3)
     }
-    // ---- split of the next step: rank its keys (drawn during this step's first accept phase).  (Spreading the binned
-    //      ranking over the barriers of the second half-step, as the warp-private kernel does, measured 2-3 % slower
-    //      here: the per-warp scan lands on the accept phase of all eight warps.) ------------------------------------
+    // ---- split of the next step: rank its keys (drawn during this step's first accept phase; bin slots taken in the
+    //      second one): scan | barrier | placement | barrier | count.  (Spreading ALL of the binned ranking over the
+    //      barriers of the second half-step, as the warp-private kernel does, measured 2-3 % slower here: the per-warp
+    //      scan lands on the accept phase of all eight warps.) ---------------------------------------------------------
     if (binned) {
-      rank_keys_binned<NT>(s.keys, list_next, W, s.hist, s.sorted);
+      if (!kRankInAccept) {                          // bin slots in a phase of their own (one more barrier)
+        rk_key = 0; rk_bin = 0; rk_slot = 0;
+        if (tid < W) {
+          rk_key = s.keys[tid];
+          rk_bin = (int)(rk_key >> 24);
+          rk_slot = atomicAdd(&s.hist[rk_bin], 1);
+        }
+        __syncthreads();
+      }
+      rank_binned_rest<NT>(list_next, W, s.hist, s.sorted, rk_key, rk_bin, rk_slot);
     } else {
       side.begin(s.keys, list_next, W, 0);
       side.finish();
     }
     PHASE_MARK(0)
-    // (the proposals of the next step read list_next and coords: synchronise here)
+    // the proposals of the next step read list_next: synchronise here (round 2c: once — this barrier was doubled)
     __syncthreads();
-    // ---- backend.save_step: chain[it] = coords ; log_prob[it] = lp -----------------------------
-    // (no barrier needed in between: the next reader of list_next / coords is behind the barrier
-    //  that ends the next PROPOSE phase... the proposals read list_next, so synchronise here)
-    __syncthreads();
+    // ---- backend.save_step: chain[it] = coords ; log_prob[it] = lp (reads only; the next writer of coords / lp is the
+    //      next accept phase, two barriers away) -----------------------------------------------------------------------
     if (it >= first && (it - first) % P.thin == 0) {
       if (P.chain != nullptr && writer) {
         double* dst = P.chain + ((size_t)b * P.nkeep + kept) * W * ndim;
