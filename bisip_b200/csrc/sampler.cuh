@@ -188,6 +188,60 @@ __device__ __forceinline__ bool propose_and_check(const double* __restrict__ cj,
   return ok;
 }
 
+// q = c - (c - s) * zz for the dimensions d = sub, sub + 2, ... of one proposal (the two lanes of a row share it);
+// returns this lane's part of the strict-prior flag.  Fully unrolled per ndim like propose_and_check_n.
+template <int ND>
+__device__ __forceinline__ bool propose_pair_n(const double* __restrict__ cj, const double* __restrict__ sk, double zz,
+                                               double* __restrict__ dst, const long long* __restrict__ bkey, int sub) {
+  constexpr int H = (ND + 1) / 2;
+  double c[H], x[H];
+  long long lo[H], hi[H];
+#pragma unroll
+  for (int i = 0; i < H; ++i) {
+    const int d = 2 * i + sub;
+    const int dd = d < ND ? d : 0;
+    c[i] = cj[dd];
+    x[i] = sk[dd];
+    lo[i] = bkey[dd];
+    hi[i] = bkey[ND + dd];
+  }
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < H; ++i) {
+    const int d = 2 * i + sub;
+    const double v = __dsub_rn(c[i], __dmul_rn(__dsub_rn(c[i], x[i]), zz));
+    const long long k = ordered_key(v);
+    if (d < ND) {
+      dst[d] = v;
+      ok = ok & (lo[i] < k) & (k < hi[i]);
+    }
+  }
+  return ok;
+}
+
+__device__ __forceinline__ bool propose_pair(const double* __restrict__ cj, const double* __restrict__ sk, double zz,
+                                             double* __restrict__ dst, const long long* __restrict__ bkey, int ndim, int sub) {
+  switch (ndim) {
+    case 2: return propose_pair_n<2>(cj, sk, zz, dst, bkey, sub);
+    case 3: return propose_pair_n<3>(cj, sk, zz, dst, bkey, sub);
+    case 4: return propose_pair_n<4>(cj, sk, zz, dst, bkey, sub);
+    case 5: return propose_pair_n<5>(cj, sk, zz, dst, bkey, sub);
+    case 6: return propose_pair_n<6>(cj, sk, zz, dst, bkey, sub);
+    case 7: return propose_pair_n<7>(cj, sk, zz, dst, bkey, sub);
+    case 8: return propose_pair_n<8>(cj, sk, zz, dst, bkey, sub);
+    case 9: return propose_pair_n<9>(cj, sk, zz, dst, bkey, sub);
+    default: break;
+  }
+  bool ok = true;
+  for (int d = sub; d < ndim; d += 2) {
+    const double v = __dsub_rn(cj[d], __dmul_rn(__dsub_rn(cj[d], sk[d]), zz));
+    dst[d] = v;
+    const long long k = ordered_key(v);
+    ok = ok & (bkey[d] < k) & (k < bkey[ndim + d]);
+  }
+  return ok;
+}
+
 // Accept filter on the integer pipe.  est = (lp' - lp) + lf is the FP32-logarithm image of emcee's
 // (ndim-1) ln zz + lp' - lp - ln u, whose error is < 1e-5 from the logarithms plus the FP64 rounding of the two
 // log-probabilities (<= 2^-52 (|lp'| + |lp|)).  The FP64 decision is therefore already determined whenever
@@ -759,6 +813,11 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
 
   uint32_t rk_key = 0;
   int rk_bin = 0, rk_slot = 0;
+#ifdef BISIP_PAIR_PROPOSE
+  constexpr bool kPairPropose = BISIP_PAIR_PROPOSE != 0;
+#else
+  constexpr bool kPairPropose = Eval::kClustered;   // same-box A/B (profiles/r02d_barriers.md): clustered evaluators +0.4-1 %, TF32 tcgen05 -2 %
+#endif
   // bin slots of the key ranking inside the second accept phase (one CTA barrier less per step) or in a phase of their
   // own: +-1-2 % either way depending on the evaluator and the CTA size (profiles/r02d_barriers.md)
 #ifdef BISIP_RANK_IN_ACCEPT
@@ -781,11 +840,27 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
       //      under the previous evaluation).  Second half-step: every thread also takes the bin slot of its key of the
       //      NEXT step's split (keys drawn in the first accept phase) — the ranking rides on the barriers that exist ----
       FINE_START
-      for (int q = tid; q < Hs; q += NT) {
-        const int j = list[coff + s.partner[q]];
-        const int k = list[off + q];
-        s.inb[q] = propose_and_check(s.coords + j * ndim, s.coords + k * ndim, zzb[q], s.prop + q * ndim, s.bkey, ndim) ? 1 : 0;
-        ev.prepare_row(q, s.prop + q * ndim);
+      if (kPairPropose && 2 * Hs <= NT && !Eval::kNeedsPrepare) {
+        // two threads per proposal, the dimensions interleaved between them (round 2d: the threads beyond Hs idled here
+        // and the dependent chain of one thread per proposal was ~1,400 cycles for six dimensions); same arithmetic per
+        // dimension, so positions stay bit-identical.  Used by the clustered evaluators only (kPairPropose); never for the
+        // vector models: their row constants (exp, sincospi, divisions) would be prepared on half-filled warps.
+        const int q = tid >> 1, sub = tid & 1;
+        bool ok = true;
+        if (q < Hs) {
+          const int j = list[coff + s.partner[q]];
+          const int k = list[off + q];
+          ok = propose_pair(s.coords + j * ndim, s.coords + k * ndim, zzb[q], s.prop + q * ndim, s.bkey, ndim, sub);
+        }
+        const unsigned okm = __ballot_sync(0xffffffffu, ok);
+        if (q < Hs && sub == 0) s.inb[q] = ((okm >> ((tid & 31) & ~1)) & 3u) == 3u ? 1 : 0;
+      } else {
+        for (int q = tid; q < Hs; q += NT) {
+          const int j = list[coff + s.partner[q]];
+          const int k = list[off + q];
+          s.inb[q] = propose_and_check(s.coords + j * ndim, s.coords + k * ndim, zzb[q], s.prop + q * ndim, s.bkey, ndim) ? 1 : 0;
+          ev.prepare_row(q, s.prop + q * ndim);
+        }
       }
       FINE_MARK(6)
       __syncthreads();

@@ -313,60 +313,6 @@ __device__ __forceinline__ double* wp_eval_carve(VecWarpEvaluator<Row, ILP>& ev,
 template <int KC>
 __device__ __forceinline__ double* wp_eval_carve(DecompMmaWarpEvaluator<KC>& ev, double* base, int) { return ev.carve(base); }
 
-// q = c - (c - s) * zz for the dimensions d = sub, sub + 2, ... of one proposal (the two lanes of a row share it);
-// returns this lane's part of the strict-prior flag.  Fully unrolled per ndim like propose_and_check_n.
-template <int ND>
-__device__ __forceinline__ bool propose_pair_n(const double* __restrict__ cj, const double* __restrict__ sk, double zz,
-                                               double* __restrict__ dst, const long long* __restrict__ bkey, int sub) {
-  constexpr int H = (ND + 1) / 2;
-  double c[H], x[H];
-  long long lo[H], hi[H];
-#pragma unroll
-  for (int i = 0; i < H; ++i) {
-    const int d = 2 * i + sub;
-    const int dd = d < ND ? d : 0;
-    c[i] = cj[dd];
-    x[i] = sk[dd];
-    lo[i] = bkey[dd];
-    hi[i] = bkey[ND + dd];
-  }
-  bool ok = true;
-#pragma unroll
-  for (int i = 0; i < H; ++i) {
-    const int d = 2 * i + sub;
-    const double v = __dsub_rn(c[i], __dmul_rn(__dsub_rn(c[i], x[i]), zz));
-    const long long k = ordered_key(v);
-    if (d < ND) {
-      dst[d] = v;
-      ok = ok & (lo[i] < k) & (k < hi[i]);
-    }
-  }
-  return ok;
-}
-
-__device__ __forceinline__ bool propose_pair(const double* __restrict__ cj, const double* __restrict__ sk, double zz,
-                                             double* __restrict__ dst, const long long* __restrict__ bkey, int ndim, int sub) {
-  switch (ndim) {
-    case 2: return propose_pair_n<2>(cj, sk, zz, dst, bkey, sub);
-    case 3: return propose_pair_n<3>(cj, sk, zz, dst, bkey, sub);
-    case 4: return propose_pair_n<4>(cj, sk, zz, dst, bkey, sub);
-    case 5: return propose_pair_n<5>(cj, sk, zz, dst, bkey, sub);
-    case 6: return propose_pair_n<6>(cj, sk, zz, dst, bkey, sub);
-    case 7: return propose_pair_n<7>(cj, sk, zz, dst, bkey, sub);
-    case 8: return propose_pair_n<8>(cj, sk, zz, dst, bkey, sub);
-    case 9: return propose_pair_n<9>(cj, sk, zz, dst, bkey, sub);
-    default: break;
-  }
-  bool ok = true;
-  for (int d = sub; d < ndim; d += 2) {
-    const double v = __dsub_rn(cj[d], __dmul_rn(__dsub_rn(cj[d], sk[d]), zz));
-    dst[d] = v;
-    const long long k = ordered_key(v);
-    ok = ok & (bkey[d] < k) & (k < bkey[ndim + d]);
-  }
-  return ok;
-}
-
 template <class Eval, int MINB, int NT>
 __global__ void __launch_bounds__(NT, MINB) ensemble_wp_kernel(const EnsembleParams P) {
   extern __shared__ __align__(16) double smem[];
