@@ -509,6 +509,7 @@ template <int KC>
 struct DecompEvaluator {
   static constexpr bool kClustered = false;
   static constexpr bool kRankInAccept = true;
+  static constexpr bool kLegacyRank = false;
   static constexpr bool kNeedsPrepare = false;
   __device__ __forceinline__ void prepare_row(int, const double*) {}
   __device__ __forceinline__ void release() {}
@@ -536,6 +537,7 @@ struct DecompEvaluator {
 struct DecompRCEvaluator {
   static constexpr bool kClustered = true;
   static constexpr bool kRankInAccept = false;     // measured: 3.712e8 vs 3.691e8 at 256 taus (profiles/r02d_barriers.md)
+  static constexpr bool kLegacyRank = false;
   static constexpr bool kNeedsPrepare = false;
   __device__ __forceinline__ void prepare_row(int, const double*) {}
   __device__ __forceinline__ void release() {}
@@ -565,6 +567,7 @@ template <int PREC>
 struct DecompTF32Evaluator {
   static constexpr bool kClustered = true;
   static constexpr bool kRankInAccept = true;
+  static constexpr bool kLegacyRank = false;
   static constexpr bool kNeedsPrepare = false;
   __device__ __forceinline__ void prepare_row(int, const double*) {}
   __device__ __forceinline__ void release() {}
@@ -595,6 +598,7 @@ template <int PREC, bool CL = false>
 struct DecompUmmaEvaluator {
   static constexpr bool kClustered = CL;
   static constexpr bool kRankInAccept = true;      // TF32 8.38e9 vs 8.32e9, 3xTF32 equal
+  static constexpr bool kLegacyRank = false;
   static constexpr bool kNeedsPrepare = false;
   __device__ __forceinline__ void prepare_row(int, const double*) {}
   DecompUmmaSmem sm;
@@ -622,6 +626,7 @@ struct DecompUmmaEvaluator {
 struct DecompCollapsedEvaluator {
   static constexpr bool kClustered = false;
   static constexpr bool kRankInAccept = true;
+  static constexpr bool kLegacyRank = false;
   static constexpr bool kNeedsPrepare = false;
   __device__ __forceinline__ void prepare_row(int, const double*) {}
   __device__ __forceinline__ void release() {}
@@ -658,6 +663,7 @@ template <class Row, int ILP = 2>
 struct VecEvaluator {
   static constexpr bool kClustered = false;
   static constexpr bool kRankInAccept = Row::kRankInAccept;
+  static constexpr bool kLegacyRank = Row::kLegacyRank;
   static constexpr bool kNeedsPrepare = true;
   VecSmem sm;
   int N, n_modes;
@@ -813,6 +819,15 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
 
   uint32_t rk_key = 0;
   int rk_bin = 0, rk_slot = 0;
+  // The Dias and Cole-Cole kernels (6-8 CTAs per SM) are FASTER with the round-1 sequence of 12 barriers per step, the
+  // doubled one included (same-box A/B, profiles/r02d_barriers.md: Dias, 128 walkers, 7.01e9 vs 6.95e9 on full waves, 6.30e9
+  // vs 6.06e9 on the 1,024 spectra of BASELINE config 3; Shin is 0.6 % faster with the short one): their barriers are free
+  // (other CTAs fill them) and apparently keep the co-resident CTAs out of phase.
+#ifdef BISIP_LEGACY_RANK
+  constexpr bool kLegacyRank = BISIP_LEGACY_RANK != 0;
+#else
+  constexpr bool kLegacyRank = Eval::kLegacyRank;
+#endif
 #ifdef BISIP_PAIR_PROPOSE
   constexpr bool kPairPropose = BISIP_PAIR_PROPOSE != 0;
 #else
@@ -906,10 +921,10 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
       FINE_MARK(10)
       if (sp == 0) {
         gen_keys(t + 1u, tid, NT);
-        if (binned)                                  // bin counters of the ranking at the end of this step (last read: the
+        if (binned && !kLegacyRank)                  // bin counters of the ranking at the end of this step (last read: the
           for (int i = tid; i < 256; i += NT) s.hist[i] = 0;   // previous step's ranking, two barriers ago)
       }
-      else if (binned && kRankInAccept) {
+      else if (binned && kRankInAccept && !kLegacyRank) {
         // second half-step: bin slot of this thread's key of the NEXT step's split (keys drawn and counters zeroed one
         // half-step ago) — the first of the ranking's barriers is the one that ends this accept phase
         rk_key = 0; rk_bin = 0; rk_slot = 0;
@@ -927,7 +942,10 @@ __global__ void __launch_bounds__(NT, MINB) ensemble_kernel(const EnsembleParams
     //      second one): scan | barrier | placement | barrier | count.  (Spreading ALL of the binned ranking over the
     //      barriers of the second half-step, as the warp-private kernel does, measured 2-3 % slower here: the per-warp
     //      scan lands on the accept phase of all eight warps.) ---------------------------------------------------------
-    if (binned) {
+    if (binned && kLegacyRank) {
+      rank_keys_binned<NT>(s.keys, list_next, W, s.hist, s.sorted);     // 4 barriers inside
+      __syncthreads();                               // (and the doubled barrier below: see kLegacyRank)
+    } else if (binned) {
       if (!kRankInAccept) {                          // bin slots in a phase of their own (one more barrier)
         rk_key = 0; rk_bin = 0; rk_slot = 0;
         if (tid < W) {
