@@ -86,7 +86,8 @@ def gather_packed(local, n_total, rank, world, group=None):
     keys = sorted(local)
     first = local[keys[0]]
     n_loc = first.shape[0]
-    cols = [local[k].reshape(n_loc, -1).to(torch.float64) for k in keys]
+    # explicit widths: a rank whose shard is empty (fewer spectra than ranks) still takes part in the collective
+    cols = [local[k].reshape(n_loc, int(np.prod(local[k].shape[1:], dtype=np.int64))).to(torch.float64) for k in keys]
     widths = [c.shape[1] for c in cols]
     pad = torch.zeros((per, sum(widths)), dtype=torch.float64, device=first.device)
     pad[:n_loc] = torch.cat(cols, 1)
@@ -163,6 +164,7 @@ def fit_sharded(model, w, zn, zn_err, discard=0, thin=1, percentiles=(2.5, 50, 9
     out['shard'] = (lo, hi)
     inv.results, inv.percentiles = out, tuple(float(q) for q in percentiles)
     out['inversion'] = inv
+    inv._apply_nan_policy(out['flags'])         # on the complete result: every rank warns / raises alike
     return out
 
 
@@ -281,15 +283,18 @@ class BatchInversion:
         dev_res = self.fit_device(p0, discard, thin, percentiles, keep_chain, batch_size, _chain_to_host=True)
         self.percentiles = tuple(float(q) for q in percentiles)
         self.results = {k: (v if isinstance(v, np.ndarray) else v.cpu().numpy()) for k, v in dev_res.items()}
-        bad = int(np.count_nonzero(self.results['flags']))
+        self._apply_nan_policy(self.results['flags'])
+        return self.results
+
+    def _apply_nan_policy(self, flags):
+        bad = int(np.count_nonzero(flags))
         if bad and self.nan_policy != 'ignore':
-            msg = (f"Probability function returned NaN for {bad} of {self.n_spectra} spectra "
+            msg = (f"Probability function returned NaN for {bad} of {len(flags)} spectra "
                    "(results['flags'] != 0; emcee raises ValueError for a single spectrum)")
             if self.nan_policy == 'raise':
                 raise ValueError(msg)
             import warnings
             warnings.warn(msg, RuntimeWarning)
-        return self.results
 
     def fit_gathered(self, n_total, p0=None, discard=0, thin=1, percentiles=(2.5, 50, 97.5), group=None, batch_size=None):
         """``fit`` for a shard-local inversion inside a ``torch.distributed`` job: this object holds spectra
@@ -302,6 +307,7 @@ class BatchInversion:
             dev_res = gather_packed(dev_res, int(n_total), dist.get_rank(group), dist.get_world_size(group), group)
         self.percentiles = tuple(float(q) for q in percentiles)
         self.results = {k: v.cpu().numpy() for k, v in dev_res.items()}
+        self._apply_nan_policy(self.results['flags'])
         return self.results
 
     def fit_device(self, p0=None, discard=0, thin=1, percentiles=(2.5, 50, 97.5), keep_chain=False,
@@ -313,6 +319,16 @@ class BatchInversion:
         if nk == 0:
             raise ValueError('discard/thin leave no samples')
         self._validate(p0)
+        if B == 0:                              # an empty shard (fewer spectra than ranks): nothing to launch
+            f64 = dict(dtype=torch.float64, device=self.device)
+            out = {'percentiles': torch.empty((0, len(percentiles), ndim), **f64), 'mean': torch.empty((0, ndim), **f64),
+                   'std': torch.empty((0, ndim), **f64), 'acceptance_fraction': torch.empty((0,), **f64),
+                   'flags': torch.empty((0,), dtype=torch.int32, device=self.device)}
+            if keep_chain:
+                out['chain'], out['log_prob'] = torch.empty((0, nk, W, ndim), **f64), torch.empty((0, nk, W), **f64)
+                if _chain_to_host:
+                    out['chain'], out['log_prob'] = out['chain'].numpy(force=True), out['log_prob'].numpy(force=True)
+            return out
         bs = int(batch_size) if batch_size else self.max_batch(nk, keep_chain)
         bounds = _lib.dev_f64(self.param_bounds, self.device)
         shared_w = self.w.ndim == 1
@@ -355,6 +371,8 @@ class BatchInversion:
             raise AssertionError('Model is not fitted! Fit the model to a dataset before attempting to plot results.')
         a = self.results['mean'] if stat == 'mean' else self.results['percentiles'][:, int(stat)]
         lt = self.log_taus
+        if lt.ndim == 3 and a.shape[0] != lt.shape[0] and 'shard' in self.results:
+            a = a[slice(*self.results['shard'])]      # after fit_sharded with per-spectrum grids: this rank's block
         m = (relaxation_time_distribution(a[:, 1:], lt) if lt.ndim == 2 else
              np.stack([relaxation_time_distribution(a[b, 1:], lt[b]) for b in range(a.shape[0])]))
         return m, m.sum(-1)

@@ -331,6 +331,15 @@ if rank == 0:
     np.testing.assert_array_equal(res["chain"][:, 1, 3, 2], np.arange(B))
 else:
     assert res["chain"] is None
+# fewer spectra than ranks: rank 1 owns an empty block and still takes part in every collective
+import warnings
+with warnings.catch_warnings(record=True) as caught:
+    warnings.simplefilter("always")
+    one = bisip_b200.fit_sharded("dias", w, zn[:1], ze[:1], discard=2, p0=p0[:1], gather_chain=True, nwalkers=12, nsteps=10)
+assert one["shard"] == ((0, 1) if rank == 0 else (1, 1))
+assert one["mean"].shape == (1, 5) and one["percentiles"].shape == (1, 3, 5) and one["flags"].tolist() == [1]
+assert (one["chain"].shape == (1, 4, 12, 5)) if rank == 0 else (one["chain"] is None)
+assert any("returned NaN for 1 of 1" in str(c.message) for c in caught)      # nan_policy sees the complete result
 # tiny chunks: several collective rounds, ragged last shard
 ch = torch.arange(*batch.shard_range(B, rank, world), dtype=torch.float64)[:, None] * torch.ones(1, 7, dtype=torch.float64)
 full = batch.gather_chain_to_rank0(ch, B, rank, world, chunk_bytes=2 * 7 * 8)
@@ -399,6 +408,9 @@ def test_batch_validation_and_run_mcmc_kwargs(monkeypatch):
         BatchInversion('dias', w, zn, ze, nwalkers=16, nsteps=10).fit_device(p0=p0)
     with pytest.raises(ValueError):
         BatchInversion('dias', w, zn, ze, nan_policy='maybe')
+    empty = BatchInversion('dias', w, zn[:0], ze[:0], nwalkers=16, nsteps=10).fit_device(discard=4, keep_chain=True)
+    assert empty['percentiles'].shape == (0, 3, 5) and empty['chain'].shape == (0, 6, 16, 5)
+    assert empty['flags'].dtype == torch.int32 and empty['log_prob'].shape == (0, 6, 16)
     from bisip_b200 import engine
     s = EnsembleSampler(16, 5, engine.ModelSpec(model=_lib.MODEL_DIAS, ndim=5), w, zn[0], ze[0], np.zeros((2, 5)), seed=1)
     with pytest.raises(NotImplementedError, match='thin_by'):
