@@ -14,6 +14,8 @@ the *global* spectrum index, so results do not depend on ``G`` or on the sub-bat
 (``gather_packed``: one NCCL all-gather of the packed summaries; ``gather_chain_to_rank0``: optional chunked gather of
 the kept chains).  ``gather`` is the per-tensor variant (NCCL on GPU tensors; gloo on CPU tensors in the unit tests).
 """
+import os
+
 import numpy as np
 import torch
 
@@ -244,11 +246,24 @@ class BatchInversion:
         lob, hib = self.param_bounds
         g0, g1 = self.spectrum_offset + lo, self.spectrum_offset + hi
         nb = self.P0_BLOCK
-        for blk in range(g0 // nb, (g1 + nb - 1) // nb):
+
+        def fill(blk):
             rng = np.random.default_rng([self.seed, blk])
             block = rng.uniform(lob, hib, (nb, self.nwalkers, self.ndim))
             a, b = max(g0, blk * nb), min(g1, (blk + 1) * nb)
             out[a - g0:b - g0] = block[a - blk * nb:b - blk * nb]
+
+        blocks = range(g0 // nb, (g1 + nb - 1) // nb)
+        # the blocks are independent generators writing disjoint rows and NumPy fills without the GIL: a shard's draw
+        # (154 MB at the C5 shape) is host time in front of the first launch, so it runs on a few threads
+        nthreads = min(8, len(blocks) // 4, max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))))
+        if nthreads > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(nthreads) as ex:
+                list(ex.map(fill, blocks))
+        else:
+            for blk in blocks:
+                fill(blk)
         return out
 
     def _validate(self, p0):

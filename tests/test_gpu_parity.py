@@ -57,6 +57,44 @@ def test_forward_and_logprob_match_oracle(case, gold_fl, gold_ld, data_files):
     assert lp_err(lp, prob.log_probability(th)).max() <= TOL
 
 
+def test_drop_in_classes_match_live_reference_shape_sweep(data_files):
+    """The drop-in classes against the LIVE unmodified reference (oracle/_ref travels to the GPU box) on the same theta
+    and data over the axes the goldens do not span: all six bundled files, polynomial degrees 0-9 with Debye / Warburg /
+    fractional exponents, 1-5 Cole-Cole modes, thetas on the faces of the box and outside it.  Same constructor
+    arguments, same attribute names, same call signatures on both sides."""
+    from oracle import refload
+    if not refload.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    import bisip_b200 as bb
+    ref = refload.load()
+    rng = np.random.default_rng(11)
+    files = ['SIP-K389170', 'SIP-K389172', 'SIP-K389173', 'SIP-K389174', 'SIP-K389175', 'SIP-K389176']
+    ctors = [('PolynomialDecomposition', dict(poly_deg=d, c_exp=c))
+             for d, c in ((0, 1.0), (1, 0.5), (2, 1.0), (3, 0.7), (5, 0.5), (7, 1.0), (9, 1.0))]
+    ctors += [('PeltonColeCole', dict(n_modes=k)) for k in (1, 2, 3, 4, 5)] + [('Dias2000', {}), ('Shin2015', {})]
+    for i, (cls, kw) in enumerate(ctors):
+        name = files[i % len(files)]
+        r = getattr(ref, cls)(refload.data_file(name), **kw)
+        m = getattr(bb, cls)(data_files[name], **kw)
+        assert m.param_names == r.param_names
+        np.testing.assert_array_equal(m.param_bounds, r.param_bounds)
+        for key in ('w', 'zn', 'zn_err'):
+            np.testing.assert_array_equal(m.data[key], r.data[key])
+        B = r.param_bounds
+        th = rng.uniform(B[0], B[1], (40, B.shape[1]))
+        if cls == 'PolynomialDecomposition':
+            th[20:, 1:] *= 0.02           # coefficients of realistic size as well as the full box
+        th[0, 0] = B[0, 0]                # on the lower face
+        th[1, -1] = B[1, -1]              # on the upper face
+        th[2, 0] = B[1, 0] + 0.5          # outside
+        Zr = np.stack([r.forward(t, r.data['w']) for t in th])
+        lr = np.array([r._log_probability(t, r.forward, B, r.data['w'], r.data['zn'], r.data['zn_err']) for t in th])
+        assert normwise(m.forward(th, m.data['w']), Zr).max() <= TOL, (cls, kw)
+        lp = m._log_probability(th, m.forward, m.param_bounds, m.data['w'], m.data['zn'], m.data['zn_err'])
+        assert np.array_equal(np.isneginf(lp), np.isneginf(lr)) and np.isneginf(lr[:3]).all()
+        assert lp_err(lp, lr).max() <= TOL, (cls, kw)
+
+
 def test_survey_known_answers(gold_fl, data_files):
     """SURVEY.md App. C.1 log-probabilities."""
     known = {'decomp_p4_debye': 384.579610803116, 'decomp_p4_warburg': -26.40360134097351,

@@ -222,6 +222,27 @@ def test_synthetic_generator_is_shard_independent():
     assert np.allclose(np.max(np.hypot(a['zn'][:, 0], a['zn'][:, 1]), axis=1), 1.0)
 
 
+def test_draw_p0_depends_on_global_index_only(monkeypatch):
+    """Starting positions of a spectrum are a function of (seed, global index): the same whatever the shard, the sub-batch
+    or the number of host threads that drew them (BatchInversion.draw_p0 fills blocks of 64 indices in parallel)."""
+    import torch
+    from bisip_b200 import _lib
+    from bisip_b200.batch import BatchInversion
+    monkeypatch.setattr(_lib, 'require_cuda', lambda device=None: torch.device('cpu'))
+    w = np.logspace(3, -1, 8)
+    mk = lambda n, off: BatchInversion('dias', w, np.zeros((n, 2, 8)), np.ones((n, 2, 8)), nwalkers=12, nsteps=5, seed=3,
+                                       spectrum_offset=off)
+    monkeypatch.setenv('LOCAL_WORLD_SIZE', '1')
+    full = mk(1000, 0).draw_p0(0, 1000)                  # 16 blocks: threaded
+    lo, hi = mk(1, 0).param_bounds
+    assert full.shape == (1000, 12, 5) and np.all(full >= lo) and np.all(full < hi)
+    monkeypatch.setenv('LOCAL_WORLD_SIZE', '1000000')     # one thread
+    np.testing.assert_array_equal(mk(1000, 0).draw_p0(0, 1000), full)
+    np.testing.assert_array_equal(mk(300, 450).draw_p0(0, 300), full[450:750])       # another shard
+    np.testing.assert_array_equal(mk(1000, 0).draw_p0(63, 130), full[63:130])         # a sub-batch across block edges
+    assert not np.array_equal(full[0], full[64])
+
+
 def test_shard_range_partitions():
     from bisip_b200.batch import shard_range
     for n in (1, 7, 8, 100000, 12501):

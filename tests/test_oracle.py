@@ -71,6 +71,37 @@ def test_c_oracle_matches_live_reference(gold_fl, gold_ld):
             assert lp_err(prob.log_probability(t), ref) <= 1e-14
 
 
+@pytest.mark.skipif(not refload.available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_c_oracle_matches_live_reference_shape_sweep():
+    """The restatement against the live reference over the model-size axes the goldens do not span: all six bundled data
+    files, polynomial degrees 0-9 with Debye / Warburg / fractional exponents, 1-5 Cole-Cole modes, and thetas on the
+    faces of the box and outside it (strict prior: -inf without a forward call, reference models.py:64-76)."""
+    bisip = refload.load()
+    rng = np.random.default_rng(11)
+    files = ['SIP-K389170', 'SIP-K389172', 'SIP-K389173', 'SIP-K389174', 'SIP-K389175', 'SIP-K389176']
+    ctors = [('decomp', dict(poly_deg=d, c_exp=c)) for d, c in ((0, 1.0), (1, 0.5), (2, 1.0), (3, 0.7), (5, 0.5), (7, 1.0), (9, 1.0))]
+    ctors += [('colecole', dict(n_modes=k)) for k in (1, 2, 3, 4, 5)] + [('dias', {}), ('shin', {})]
+    cls = {'decomp': bisip.PolynomialDecomposition, 'colecole': bisip.PeltonColeCole, 'dias': bisip.Dias2000,
+           'shin': bisip.Shin2015}
+    for i, (model, kw) in enumerate(ctors):
+        m = cls[model](refload.data_file(files[i % len(files)]), **kw)
+        B = m.param_bounds
+        prob = oracle.Problem(model, m.data['w'], m.data['zn'], m.data['zn_err'], B, n_modes=kw.get('n_modes', 1),
+                              taus=getattr(m, 'taus', None), log_taus=getattr(m, 'log_taus', None), c_exp=kw.get('c_exp', 1.0))
+        th = rng.uniform(B[0], B[1], (12, B.shape[1]))
+        if model == 'decomp':            # coefficients of realistic size too (the full box gives |Z| ~ 1e3 and more)
+            th[6:, 1:] *= 0.02
+        th[0, 0] = B[0, 0]               # on the lower face
+        th[1, -1] = B[1, -1]             # on the upper face
+        th[2, 0] = B[1, 0] + 0.5         # outside
+        for t in th:
+            Zr = m.forward(t, m.data['w'])
+            assert normwise(prob.forward(t)[None], Zr[None]).max() <= 1e-15, (model, kw)
+            ref = m._log_probability(t, m.forward, B, m.data['w'], m.data['zn'], m.data['zn_err'])
+            assert lp_err(prob.log_probability(t), ref) <= 1e-13, (model, kw)
+        assert np.isneginf([prob.log_probability(t) for t in th[:3]]).all()
+
+
 def test_oracle_sampler_semantics(gold_fl, gold_ld):
     """Storage/slicing of the C sampler and invariants of the stretch move."""
     prob = oracle_problem('colecole_k1', gold_fl, gold_ld)
