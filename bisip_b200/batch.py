@@ -276,9 +276,6 @@ class BatchInversion:
         if p0 is not None:
             if tuple(p0.shape) != (self.n_spectra, self.nwalkers, self.ndim):
                 raise ValueError("incompatible input dimensions {0}".format(tuple(p0.shape)))
-            fin = torch.isfinite(p0).all() if isinstance(p0, torch.Tensor) else np.isfinite(p0).all()
-            if not bool(fin):
-                raise ValueError("At least one parameter value was infinite or NaN")
 
     def max_batch(self, n_keep, keep_chain):
         free, _ = torch.cuda.mem_get_info(self.device)
@@ -356,7 +353,14 @@ class BatchInversion:
             y = self._to_dev(self._zn, lo, hi)
             ye = self._to_dev(self._zn_err, lo, hi)
             w = w_all if shared_w else _lib.dev_f64(self.w[lo:hi], self.device)
-            coords = self._to_dev(p0, lo, hi).clone() if p0 is not None else _lib.dev_f64(self.draw_p0(lo, hi), self.device)
+            if p0 is not None:
+                coords = self._to_dev(p0, lo, hi).clone()
+                # emcee's finiteness check, on the device copy (a host pass over a C5 shard's 154 MB costs more than the
+                # upload) and before this sub-batch is sampled
+                if not bool(torch.isfinite(coords).all()):
+                    raise ValueError("At least one parameter value was infinite or NaN")
+            else:
+                coords = _lib.dev_f64(self.draw_p0(lo, hi), self.device)
             res = engine.ensemble_run(self._spec(lo, hi), coords, w, y, ye, bounds, nsteps=self.nsteps, seed=self.seed,
                                       spectrum0=self.spectrum_offset + lo, a=self.a, discard=discard, thin=thin,
                                       store_chain=True, store_logp=keep_chain)

@@ -426,7 +426,7 @@ def test_batch_validation_and_run_mcmc_kwargs(monkeypatch):
         BatchInversion('dias', w, zn, ze, nwalkers=16, nsteps=10).fit_device(p0=np.zeros((3, 15, 5)))
     p0 = np.zeros((3, 16, 5)); p0[1, 2, 3] = np.nan
     with pytest.raises(ValueError, match='infinite or NaN'):
-        BatchInversion('dias', w, zn, ze, nwalkers=16, nsteps=10).fit_device(p0=p0)
+        BatchInversion('dias', w, zn, ze, nwalkers=16, nsteps=10).fit_device(p0=p0, batch_size=2)   # checked on the uploaded copy, per sub-batch, before any launch
     with pytest.raises(ValueError):
         BatchInversion('dias', w, zn, ze, nan_policy='maybe')
     empty = BatchInversion('dias', w, zn[:0], ze[:0], nwalkers=16, nsteps=10).fit_device(discard=4, keep_chain=True)
