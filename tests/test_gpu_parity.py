@@ -98,7 +98,7 @@ def test_drop_in_classes_match_live_reference_shape_sweep(data_files):
 def test_forward_on_box_faces_matches_live_reference():
     """One parameter at a time (and pairs: corners) on a face of the default box, all four models: the reference's C complex
     arithmetic is finite there (1/R = inf, 1/delta = inf, 1/(1-m) = inf ...) and the CUDA forward must return the same
-    values, not NaN (342 points; the sweep is tools/face_sweep.py)."""
+    values, not NaN — forward() and the prior-free _log_likelihood() (342 points; the sweep is tools/face_sweep.py)."""
     import importlib.util
     import os
     from oracle import refload

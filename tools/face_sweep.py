@@ -54,6 +54,14 @@ def sweep(tol=1e-12):
         Zr = np.stack([r.forward(t, r.data['w']) for t in th])
         Z = m.forward(th, m.data['w'])
         npts += len(tags)
+        # the prior-free likelihood at the same points (the fused log-probability kernel's forward, not the batched one)
+        llr = np.array([r._log_likelihood(t, r.forward, r.data['w'], r.data['zn'], r.data['zn_err']) for t in th])
+        ll = m._log_likelihood(th, m.forward, m.data['w'], m.data['zn'], m.data['zn_err'])
+        with np.errstate(invalid='ignore'):
+            ll_err = np.abs(ll - llr) / np.maximum(1.0, np.abs(llr))
+        for k in np.nonzero(~(ll_err <= tol))[0]:
+            bad.append({"model": cls, "kw": kw, "param": tags[k][0], "side": tags[k][1], "status": "log-likelihood",
+                        "err": float(ll_err[k]), "theta": th[k].tolist(), "ref0": float(llr[k]), "cuda0": float(ll[k])})
         for k, tag in enumerate(tags):
             fr, fg = np.isfinite(Zr[k]).all(), np.isfinite(Z[k]).all()
             err = None
