@@ -61,8 +61,9 @@ enum bisip_precision {
   BISIP_PREC_3XTF32_MMA = 4, /* 3xTF32, always the mma.sync tile kernel */
   BISIP_PREC_FP64_COLLAPSED = 5 /* FP64, decomposition re-associated to z = (L K) a: the theta-independent product
                                    G = L K ((poly_deg+1) x 2N) is built once per spectrum (compensated sums), one
-                                   evaluation is 2N (poly_deg+3) FMAs on the FP64 vector pipe.  Same 1e-12 parity bar as
-                                   BISIP_PREC_FP64, ~10x fewer flops; the two-stage DMMA contraction stays the default */
+                                   evaluation is 2N (poly_deg+3) FMAs: FP64 DMMA tiles of 16 proposals x 8 columns up to
+                                   256 walkers, the FP64 vector pipe above.  Same 1e-12 parity bar as BISIP_PREC_FP64,
+                                   ~10x fewer flops; the two-stage DMMA contraction stays the default (n_coef <= 8) */
 };
 
 enum bisip_status {
