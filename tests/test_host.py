@@ -466,3 +466,20 @@ def test_exp_table_constants_and_accuracy():
         ex = Decimal(float(x)).exp()
         worst = max(worst, float(abs((Decimal(chk.exp_table(float(x))) - ex) / ex)))
     assert worst < 2e-16
+
+
+def test_library_sass_uses_the_tensor_cores_it_claims():
+    """The shipped sm_100a library holds the instructions DESIGN.md says the decomposition kernels issue: FP64 DMMA tiles
+    (default and collapsed paths), tcgen05 MMAs with tensor-memory loads / stores (TF32 / 3xTF32 paths: UTCHMMA, LDTM, STTM)
+    and the mma.sync TF32 tiles of the comparison arm.  cuobjdump runs on the CPU; no GPU needed."""
+    import shutil
+    exe = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(exe):
+        pytest.skip('cuobjdump not available')
+    from bisip_b200 import _lib
+    out = subprocess.run([exe, '-sass', _lib.LIB_PATH], capture_output=True, text=True, timeout=600).stdout
+    assert 'sm_100a' in out
+    count = lambda key: sum(1 for line in out.splitlines() if key in line)
+    assert count('DMMA') >= 1000
+    assert count('UTCHMMA') >= 100 and count('LDTM') >= 100 and count('STTM') >= 50
+    assert count('HMMA.1688.F32.TF32') >= 100
