@@ -423,17 +423,23 @@ class BatchInversion:
     # ------------------------------------------------------------------ construction from files
     @classmethod
     def from_files(cls, model, filepaths, headers=1, ph_units='mrad', **kwargs):
-        """Vectorised ingest of many data files (reference ``utils.py:108-146`` applied per file).  The files must
-        hold the SAME NUMBER of frequencies (one kernel launch has one n_freq); their frequency values may differ
-        (then ``w`` is per spectrum).  Group files of different length and build one ``BatchInversion`` per group."""
-        from .utils import prepare_data
-        data = [prepare_data(np.loadtxt(fp, skiprows=headers, delimiter=','), ph_units) for fp in filepaths]
-        lengths = sorted({d['N'] for d in data})
-        if len(lengths) != 1:
-            raise ValueError(f'from_files needs files with the same number of frequencies, got N in {lengths}; '
-                             'group the files by length')
-        ws = np.stack([d['w'] for d in data])
+        """Vectorised ingest of many data files (reference ``utils.py:108-146`` applied to each file: one text-to-double pass
+        over all of them, one NumPy pass for the error propagation and the normalisation; ``zn`` / ``zn_err`` equal the
+        per-file ``load_data`` result bit for bit).  The files must hold the SAME NUMBER of frequencies (one kernel launch
+        has one n_freq); their frequency values may differ (then ``w`` is per spectrum).  Group files of different length
+        and build one ``BatchInversion`` per group.  ``inv.data[i]`` is the reference's data dict of file ``i``.  Under
+        ``torchrun`` give each rank its block: ``from_files(model, paths[lo:hi], spectrum_offset=lo, ...)`` with
+        ``lo, hi = shard_range(len(paths), rank, world)``."""
+        from .utils import BatchData, prepare_data_batch, read_tables
+        try:
+            tables = read_tables(filepaths, headers)
+        except ValueError as e:
+            if 'same number of frequencies' in str(e):
+                raise ValueError('from_files needs ' + str(e)) from None
+            raise
+        arrays = prepare_data_batch(tables, ph_units)
+        ws = arrays['w']
         w = ws[0] if np.all(ws == ws[0]) else ws
-        inv = cls(model, w, np.stack([d['zn'] for d in data]), np.stack([d['zn_err'] for d in data]), **kwargs)
-        inv.data = data
+        inv = cls(model, w, arrays['zn'], arrays['zn_err'], **kwargs)
+        inv.data = BatchData(arrays)
         return inv

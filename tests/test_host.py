@@ -30,6 +30,59 @@ def test_load_data_matches_reference(gold_ld, data_files):
     assert set(d) == {'freq', 'amp', 'pha', 'amp_err', 'pha_err', 'Z', 'Z_err', 'norm_factor', 'zn', 'zn_err', 'N', 'w'}
 
 
+def test_from_files_vectorised_ingest_is_bit_identical(gold_ld, data_files, tmp_path, monkeypatch):
+    """BatchInversion.from_files (one text-to-double pass + one vectorised prepare over all files) against the per-file
+    load_data of the drop-in classes and the goldens generated from the reference; irregular inputs take NumPy's per-file
+    path; ragged lengths raise."""
+    import torch
+    from bisip_b200 import _lib, utils
+    from bisip_b200.batch import BatchInversion
+    monkeypatch.setattr(_lib, 'require_cuda', lambda device=None: torch.device('cpu'))
+    names = ['SIP-K389170', 'SIP-K389172', 'SIP-K389173', 'SIP-K389174', 'SIP-K389175', 'SIP-K389176']
+    paths = [data_files[n] for n in names]
+    for units in ('mrad', 'rad', 'deg'):
+        inv = BatchInversion.from_files('dias', paths, ph_units=units, nwalkers=16, nsteps=10)
+        assert inv.n_spectra == 6 and inv._zn.shape == (6, 2, 20) and len(inv.data) == 6
+        for i, fp in enumerate(paths):
+            one = utils.prepare_data(np.loadtxt(fp, skiprows=1, delimiter=','), units)
+            d = inv.data[i]
+            assert set(d) == set(one) and d['N'] == one['N'] == 20
+            for k in one:
+                np.testing.assert_array_equal(d[k], one[k], err_msg=f'{names[i]} {k} {units}')     # bit-identical
+            np.testing.assert_array_equal(inv._zn[i], one['zn'])
+            np.testing.assert_array_equal(inv._zn_err[i], one['zn_err'])
+    inv = BatchInversion.from_files('dias', paths, nwalkers=16, nsteps=10)
+    for i, n in enumerate(names):
+        np.testing.assert_array_equal(inv._zn[i], gold_ld[f'{n}/zn'])
+        np.testing.assert_array_equal(inv._zn_err[i], gold_ld[f'{n}/zn_err'])
+    assert [d['norm_factor'] for d in inv.data][4] == gold_ld['SIP-K389175/norm_factor']
+    assert inv.w.ndim == 1                                   # the bundled files share their frequency grid
+    # the fast pass and the per-file path agree on what they parse
+    np.testing.assert_array_equal(utils.read_tables(paths), np.stack([np.loadtxt(fp, skiprows=1, delimiter=',') for fp in paths]))
+    # other header counts, per-spectrum frequency grids, irregular formatting (spaces, a comment line): per-file path
+    body = open(paths[4]).read().splitlines()
+    (tmp_path / 'h3.dat').write_text('\n'.join(['# a', '# b'] + body) + '\n')
+    np.testing.assert_array_equal(BatchInversion.from_files('dias', [tmp_path / 'h3.dat'], headers=3, nwalkers=16, nsteps=10)._zn[0],
+                                  gold_ld['SIP-K389175/zn'])
+    rows = [r.split(',') for r in body[1:]]
+    shifted = [body[0]] + [','.join([repr(float(r[0]) * 1.5)] + r[1:]) for r in rows]
+    (tmp_path / 'shifted.dat').write_text('\n'.join(shifted) + '\n')
+    inv2 = BatchInversion.from_files('dias', [paths[4], tmp_path / 'shifted.dat'], nwalkers=16, nsteps=10)
+    assert inv2.w.shape == (2, 20)
+    np.testing.assert_array_equal(inv2.w[1], 2 * np.pi * np.array([float(r[0]) * 1.5 for r in rows]))
+    np.testing.assert_array_equal(inv2.w[0], gold_ld['SIP-K389175/w'])
+    spaced = [body[0]] + [', '.join(r) for r in rows[:10]] + ['# comment'] + [', '.join(r) for r in rows[10:]]
+    (tmp_path / 'spaced.dat').write_text('\n'.join(spaced) + '\n')
+    np.testing.assert_array_equal(BatchInversion.from_files('dias', [tmp_path / 'spaced.dat'], nwalkers=16, nsteps=10)._zn[0],
+                                  gold_ld['SIP-K389175/zn'])
+    (tmp_path / 'short.dat').write_text('\n'.join(body[:-3]) + '\n')
+    with pytest.raises(ValueError, match='same number of frequencies'):
+        BatchInversion.from_files('dias', [paths[4], tmp_path / 'short.dat'], nwalkers=16, nsteps=10)
+    (tmp_path / 'bad.dat').write_text('\n'.join(body[:5] + ['1.0,abc,3.0,4.0,5.0'] + body[6:]) + '\n')
+    with pytest.raises(ValueError):
+        BatchInversion.from_files('dias', [tmp_path / 'bad.dat'], nwalkers=16, nsteps=10)
+
+
 def test_model_surface_matches_reference(data_files, gold_fl):
     import bisip_b200 as bb
     fp = data_files['SIP-K389175']
