@@ -47,13 +47,15 @@ def default_bounds(model, poly_deg=5, n_modes=1):
 
 
 def tau_grid(w, n_tau=None, poly_deg=5):
-    """Relaxation-time grid and power table of PolynomialDecomposition (reference
-    ``models.py:201-209``) for one frequency vector: (log_tau, taus, log_taus)."""
+    """Relaxation-time grid and power table of PolynomialDecomposition (reference ``models.py:201-209``) for one
+    frequency vector (N,) or a stack of them (B, N), vectorised over the stack with the same element-wise arithmetic (the
+    rows equal the one-vector results bit for bit): (log_tau (..., S), taus (..., S), log_taus (..., poly_deg+1, S))."""
     w = np.asarray(w, dtype=np.float64)
-    lo = np.floor(min(np.log10(1. / w)) - 1)
-    hi = np.floor(max(np.log10(1. / w)) + 1)
-    log_tau = np.linspace(lo, hi, 2 * len(w) if n_tau is None else int(n_tau))
-    log_taus = np.array([log_tau ** i for i in range(poly_deg + 1)])
+    lw = np.log10(1. / w)
+    lo = np.floor(lw.min(axis=-1) - 1)
+    hi = np.floor(lw.max(axis=-1) + 1)
+    log_tau = np.linspace(lo, hi, 2 * w.shape[-1] if n_tau is None else int(n_tau), axis=-1)
+    log_taus = np.stack([log_tau ** i for i in range(poly_deg + 1)], axis=-2)
     return log_tau, 10 ** log_tau, log_taus
 
 
@@ -208,13 +210,7 @@ class BatchInversion:
         self.poly_deg, self.c_exp, self.n_modes, self.precision = poly_deg, c_exp, n_modes, precision
         taus = log_taus = None
         if model == 'decomp':
-            if self.w.ndim == 1:
-                self.log_tau, taus, log_taus = tau_grid(self.w, n_tau, poly_deg)
-            else:
-                grids = [tau_grid(wb, n_tau, poly_deg) for wb in self.w]
-                self.log_tau = np.stack([g[0] for g in grids])
-                taus = np.stack([g[1] for g in grids])
-                log_taus = np.stack([g[2] for g in grids])
+            self.log_tau, taus, log_taus = tau_grid(self.w, n_tau, poly_deg)
         self.taus, self.log_taus = taus, log_taus
         self.results = None
 

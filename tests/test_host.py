@@ -296,6 +296,26 @@ def test_draw_p0_depends_on_global_index_only(monkeypatch):
     assert not np.array_equal(full[0], full[64])
 
 
+def test_tau_grid_matches_reference_tables_and_vectorises(data_files):
+    """batch.tau_grid builds PolynomialDecomposition's log_tau / taus / log_taus (reference models.py:201-209) — the same
+    tables the drop-in class holds (which test_model_surface_matches_reference pins to the reference's), and for a (B, N)
+    stack of frequency vectors the rows are bit-identical to the one-vector results."""
+    import bisip_b200 as bb
+    from bisip_b200.batch import tau_grid
+    m = bb.PolynomialDecomposition(data_files['SIP-K389175'], poly_deg=5)
+    lt, taus, lts = tau_grid(m.data['w'], None, 5)
+    np.testing.assert_array_equal(lt, m.log_tau)
+    np.testing.assert_array_equal(taus, m.taus)
+    np.testing.assert_array_equal(lts, m.log_taus)
+    rng = np.random.default_rng(1)
+    w = 2 * np.pi * 10 ** rng.uniform(-3, 5, (40, 33))
+    stack = tau_grid(w, 40, 7)
+    assert stack[0].shape == (40, 40) and stack[2].shape == (40, 8, 40)
+    for i in range(40):
+        for a, b in zip(stack, tau_grid(w[i], 40, 7)):
+            np.testing.assert_array_equal(a[i], b)
+
+
 def test_shard_range_partitions():
     from bisip_b200.batch import shard_range
     for n in (1, 7, 8, 100000, 12501):
